@@ -1,0 +1,16 @@
+// capi_common.hpp — definitions shared by the two halves of the C ABI (capi_host.cpp, capi_device.cu).
+#pragma once
+#include <string>
+
+#include "errors.hpp"
+#include "flat_index.hpp"
+
+struct blight_flat { blight::FlatIndex f; };
+
+namespace blight {
+extern thread_local std::string g_last_error;
+int fail(int code, const std::string& msg);
+void fill_info(const FlatIndex& f, blight_info* out);
+// Keeps MPHF groups [g_begin, g_end): other buckets become empty, arrays are compacted, ids stay global.
+int flat_slice(const FlatIndex& f, uint64_t g_begin, uint64_t g_end, FlatIndex& out, std::string* err);
+}  // namespace blight

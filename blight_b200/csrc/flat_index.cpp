@@ -1,0 +1,222 @@
+// flat_index.cpp — BLFLAT01 blob save / load / validate, FASTA record splitting.
+#include "flat_index.hpp"
+#include "errors.hpp"
+#include "capi_common.hpp"
+
+#include <zlib.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+namespace blight {
+
+namespace {
+void set_err(std::string* err, const std::string& s) { if (err) *err = s; }
+
+template <class T>
+bool write_vec(std::ofstream& os, const std::vector<T>& v, size_t pad_to = 8) {
+	if (!v.empty()) os.write(reinterpret_cast<const char*>(v.data()), std::streamsize(v.size() * sizeof(T)));
+	size_t bytes = v.size() * sizeof(T);
+	static const char zeros[8] = {0};
+	if (bytes % pad_to) os.write(zeros, std::streamsize(pad_to - bytes % pad_to));
+	return os.good();
+}
+
+template <class T>
+bool read_vec(std::ifstream& is, std::vector<T>& v, uint64_t n, size_t pad_to = 8) {
+	v.resize(n);
+	if (n) is.read(reinterpret_cast<char*>(v.data()), std::streamsize(n * sizeof(T)));
+	size_t bytes = n * sizeof(T);
+	if (bytes % pad_to) is.ignore(std::streamsize(pad_to - bytes % pad_to));
+	return is.good();
+}
+}  // namespace
+
+int flat_save(const FlatIndex& f, const std::string& path, std::string* err) {
+	std::ofstream os(path, std::ios::binary);
+	if (!os) { set_err(err, "cannot open " + path + " for writing"); return BL_ERR_IO; }
+	os.write(reinterpret_cast<const char*>(&f.h), sizeof f.h);
+	bool ok = write_vec(os, f.bucket_start) && write_vec(os, f.bucket_nuc) && write_vec(os, f.mphf) && write_vec(os, f.seq) &&
+	          write_vec(os, f.pos) && write_vec(os, f.bits) && write_vec(os, f.ranks) && write_vec(os, f.fb_keys) &&
+	          write_vec(os, f.fb_vals);
+	os.flush();
+	if (!ok || !os.good()) { set_err(err, "write failed: " + path); return BL_ERR_IO; }
+	return BL_OK;
+}
+
+int flat_load(const std::string& path, FlatIndex& f, std::string* err) {
+	std::ifstream is(path, std::ios::binary);
+	if (!is) { set_err(err, "cannot open " + path); return BL_ERR_IO; }
+	is.read(reinterpret_cast<char*>(&f.h), sizeof f.h);
+	if (!is || std::memcmp(f.h.magic, "BLFLAT01", 8) != 0) { set_err(err, "not a BLFLAT01 blob: " + path); return BL_ERR_FORMAT; }
+	const FlatHeader& h = f.h;
+	if (h.m == 0 || h.m > 15 || h.n_buckets != (1ull << (2 * h.m - 1)) || h.n_log2 > 2 * h.m - 1 || h.n_mphf != (1ull << h.n_log2)) {
+		set_err(err, "inconsistent header");
+		return BL_ERR_FORMAT;
+	}
+	bool ok = read_vec(is, f.bucket_start, h.n_buckets) && read_vec(is, f.bucket_nuc, h.n_buckets) && read_vec(is, f.mphf, h.n_mphf) &&
+	          read_vec(is, f.seq, h.seq_words) && read_vec(is, f.pos, h.pos_words) && read_vec(is, f.bits, h.bits_words_total) &&
+	          read_vec(is, f.ranks, h.ranks_total) && read_vec(is, f.fb_keys, h.fallback_total) &&
+	          read_vec(is, f.fb_vals, h.fallback_total);
+	if (!ok) { set_err(err, "truncated blob: " + path); return BL_ERR_FORMAT; }
+	return flat_validate(f, err);
+}
+
+int flat_validate(const FlatIndex& f, std::string* err) {
+	const FlatHeader& h = f.h;
+	auto bad = [&](const char* what) { set_err(err, std::string("flat index invalid: ") + what); return BL_ERR_FORMAT; };
+	if (h.k == 0 || h.k > 31) return bad("k");
+	if ((h.m & 1) == 0 || h.m > 15 || h.m > h.k) return bad("m");
+	if (h.n_log2 > 2 * h.m - 1) return bad("n");
+	if (h.b > 31) return bad("b");
+	if (f.bucket_start.size() != h.n_buckets || f.bucket_nuc.size() != h.n_buckets) return bad("bucket table size");
+	if (f.mphf.size() != h.n_mphf) return bad("mphf table size");
+	if (f.seq.size() != h.seq_words || h.seq_words != (h.total_nuc * 2 + 63) / 64) return bad("seq words");
+	if (f.pos.size() != h.pos_words || h.pos_words != (h.positions_bits + 63) / 64) return bad("pos words");
+	if (f.bits.size() != h.bits_words_total || f.ranks.size() != h.ranks_total) return bad("mphf arrays");
+	if (f.fb_keys.size() != h.fallback_total || f.fb_vals.size() != h.fallback_total) return bad("fallback arrays");
+	for (uint64_t i = 0; i < h.n_buckets; i++)
+		if (f.bucket_start[i] + f.bucket_nuc[i] > h.total_nuc) return bad("bucket extent");
+	for (const MphfRec& r : f.mphf) {
+		if (!r.present) continue;
+		if (r.bits_word_off + r.bits_nwords > h.bits_words_total) return bad("mphf bits extent");
+		if (r.ranks_off + r.nranks > h.ranks_total) return bad("mphf ranks extent");
+		if (r.fb_off + r.fb_count > h.fallback_total) return bad("mphf fallback extent");
+		if (r.nbits == 0 || r.nbits > 32) return bad("mphf nbits");
+		uint64_t tot = 0;
+		for (int l = 0; l < kLevels; l++) { if (r.dom[l] == 0 || (r.dom[l] & 63)) return bad("mphf level domain"); tot += r.dom[l]; }
+		if (tot != r.bits_nwords * 64) return bad("mphf level domains do not sum to the bit array size");
+		if (r.pos_start + r.nelem * r.nbits > h.positions_bits) return bad("mphf positions extent");
+	}
+	return BL_OK;
+}
+
+// getline()-pairing of the reference (blight.cpp:212-229 / 760-775): line A is skipped as the header whatever it
+// holds; an empty A swallows the next line too; an empty sequence line drops the record.
+void split_fasta_records(const char* text, uint64_t len, std::vector<SeqView>& seqs) {
+	uint64_t p = 0;
+	bool eof = false;
+	auto getline = [&](const char*& s, uint64_t& n) {
+		if (p >= len) { s = text + len; n = 0; eof = true; return; }
+		const char* nl = static_cast<const char*>(std::memchr(text + p, '\n', len - p));
+		s = text + p;
+		if (nl) { n = uint64_t(nl - s); p += n + 1; }
+		else { n = len - p; p = len; eof = true; }
+	};
+	while (!eof) {
+		const char* s; uint64_t n;
+		getline(s, n);
+		if (n == 0) { getline(s, n); continue; }
+		getline(s, n);
+		if (n == 0) continue;
+		seqs.push_back(SeqView{s, n});
+	}
+}
+
+int read_fasta_records(const std::string& path, std::string& storage, std::vector<SeqView>& seqs, std::string* err) {
+	gzFile gz = gzopen(path.c_str(), "rb");  // transparent for plain files, like zstr::ifstream (zstr.hpp:153-167)
+	if (!gz) { set_err(err, "Problem with files opening: " + path); return BL_ERR_IO; }
+	gzbuffer(gz, 1 << 20);
+	storage.clear();
+	std::vector<char> buf(1 << 24);
+	for (;;) {
+		int got = gzread(gz, buf.data(), unsigned(buf.size()));
+		if (got < 0) { gzclose(gz); set_err(err, "read error: " + path); return BL_ERR_IO; }
+		if (got == 0) break;
+		storage.append(buf.data(), size_t(got));
+	}
+	gzclose(gz);
+	split_fasta_records(storage.data(), storage.size(), seqs);
+	return BL_OK;
+}
+
+
+void fill_info(const FlatIndex& f, blight_info* out) {
+	std::memset(out, 0, sizeof *out);
+	const FlatHeader& h = f.h;
+	out->k = h.k; out->m = h.m; out->n_log2 = h.n_log2; out->s_log2 = h.s_log2; out->b = h.b;
+	out->n_buckets = h.n_buckets;
+	out->n_mphf = h.n_mphf;
+	out->number_kmer = h.number_kmer;
+	out->number_super_kmer = h.number_super_kmer;
+	out->total_nuc = h.total_nuc;
+	out->positions_bits = h.positions_bits;
+	out->mphf_bits = h.bits_words_total * 64;
+	out->fallback_keys = h.fallback_total;
+	for (const MphfRec& r : f.mphf) out->largest_mphf = r.nelem > out->largest_mphf ? r.nelem : out->largest_mphf;
+	for (uint32_t n : f.bucket_nuc) out->largest_bucket = n > out->largest_bucket ? n : out->largest_bucket;
+}
+
+namespace {
+// copies `nbits` bits from src starting at bit `sbit` to dst starting at bit `dbit` (dst pre-zeroed there)
+void copy_bits(const std::vector<uint64_t>& src, uint64_t sbit, std::vector<uint64_t>& dst, uint64_t dbit, uint64_t nbits) {
+	while (nbits) {
+		const unsigned so = unsigned(sbit & 63), dof = unsigned(dbit & 63);
+		unsigned take = 64 - (so > dof ? so : dof);
+		if (take > nbits) take = unsigned(nbits);
+		const uint64_t mask = take == 64 ? ~0ull : ((1ull << take) - 1);
+		const uint64_t v = (src[sbit >> 6] >> so) & mask;
+		dst[dbit >> 6] |= v << dof;
+		sbit += take; dbit += take; nbits -= take;
+	}
+}
+}  // namespace
+
+int flat_slice(const FlatIndex& f, uint64_t g0, uint64_t g1, FlatIndex& o, std::string* err) {
+	const FlatHeader& h = f.h;
+	const unsigned lb = f.lb();
+	o = FlatIndex();
+	o.h = h;
+	o.bucket_start.assign(h.n_buckets, 0);
+	o.bucket_nuc.assign(h.n_buckets, 0);
+	o.mphf.assign(h.n_mphf, MphfRec{});
+	const uint64_t b0 = g0 << lb, b1 = g1 << lb;
+	// buckets of a group range are contiguous in seq
+	const uint64_t nuc0 = b0 < h.n_buckets ? f.bucket_start[b0] : h.total_nuc;
+	const uint64_t nuc1 = b1 < h.n_buckets ? f.bucket_start[b1] : h.total_nuc;
+	// the 2^b-window scan may run past the end of a bucket into what follows (blight.cpp:729-739): keep that tail
+	// so a slice answers exactly like the whole index
+	const uint64_t tail = std::min<uint64_t>(h.total_nuc - nuc1, (1ull << h.b) + h.k);
+	o.h.total_nuc = nuc1 - nuc0 + tail;
+	o.h.seq_words = (o.h.total_nuc * 2 + 63) / 64;
+	o.seq.assign(o.h.seq_words, 0);
+	copy_bits(f.seq, nuc0 * 2, o.seq, 0, o.h.total_nuc * 2);
+	for (uint64_t b = b0; b < b1; b++) { o.bucket_start[b] = f.bucket_start[b] - nuc0; o.bucket_nuc[b] = f.bucket_nuc[b]; }
+	for (uint64_t b = 0; b < h.n_buckets; b++) if (b < b0) o.bucket_start[b] = 0; else if (b >= b1) o.bucket_start[b] = nuc1 - nuc0;
+	// positions slabs of the range are contiguous too
+	const uint64_t p0 = g0 < h.n_mphf ? f.mphf[g0].pos_start : h.positions_bits;
+	const uint64_t p1 = g1 < h.n_mphf ? f.mphf[g1].pos_start : h.positions_bits;
+	o.h.positions_bits = p1 - p0;
+	o.h.pos_words = (o.h.positions_bits + 63) / 64;
+	o.pos.assign(o.h.pos_words, 0);
+	copy_bits(f.pos, p0, o.pos, 0, o.h.positions_bits);
+	o.h.number_kmer = 0;
+	for (uint64_t g = 0; g < h.n_mphf; g++) {
+		MphfRec& r = o.mphf[g];
+		if (g < g0 || g >= g1) {
+			r = MphfRec{};
+			r.nbits = f.mphf[g].nbits;
+			r.id_offset = f.mphf[g].id_offset;
+			r.pos_start = g < g0 ? 0 : o.h.positions_bits;
+			continue;
+		}
+		r = f.mphf[g];
+		r.pos_start -= p0;
+		o.h.number_kmer += r.nelem;
+		if (!r.present) continue;
+		r.bits_word_off = o.bits.size();
+		o.bits.insert(o.bits.end(), f.bits.begin() + f.mphf[g].bits_word_off, f.bits.begin() + f.mphf[g].bits_word_off + r.bits_nwords);
+		r.ranks_off = o.ranks.size();
+		o.ranks.insert(o.ranks.end(), f.ranks.begin() + f.mphf[g].ranks_off, f.ranks.begin() + f.mphf[g].ranks_off + r.nranks);
+		r.fb_off = o.fb_keys.size();
+		o.fb_keys.insert(o.fb_keys.end(), f.fb_keys.begin() + f.mphf[g].fb_off, f.fb_keys.begin() + f.mphf[g].fb_off + r.fb_count);
+		o.fb_vals.insert(o.fb_vals.end(), f.fb_vals.begin() + f.mphf[g].fb_off, f.fb_vals.begin() + f.mphf[g].fb_off + r.fb_count);
+	}
+	o.h.bits_words_total = o.bits.size();
+	o.h.ranks_total = o.ranks.size();
+	o.h.fallback_total = o.fb_keys.size();
+	return flat_validate(o, err);
+}
+
+}  // namespace blight

@@ -1,0 +1,143 @@
+/* blight_b200.h — C ABI of the B200-native batched k-mer query path of Blight.
+ *
+ * The reference has no FFI: its boundary is the public C++ class kmer_Set_Light (blight.h:15-136).
+ * This header is what a binding for that class calls into; the C++ mirror of the class that sits on
+ * top of it is blight_b200/csrc/kmer_set_light.hpp.  Each entry point cites the reference interface
+ * it replaces.  Conventions: plain pointers and sizes, `int` status (0 = BLIGHT_OK, negative = error,
+ * text via blight_last_error()), caller owns every buffer it passes, the library owns the objects it
+ * returns until the matching *_free.  "d_" parameters are DEVICE pointers on the index's device and the
+ * call is asynchronous on `stream` (a cudaStream_t passed as void*, NULL = legacy default stream);
+ * "h_" / unprefixed buffers are host memory and those calls return when the result is in the buffer.
+ * Concurrent queries on one index from several host threads are allowed when each uses its own stream
+ * (the *_host calls serialise on an internal stream).
+ *
+ * There is no CPU fallback behind this ABI: every query entry point runs the sm_100a kernels or
+ * returns BLIGHT_ERR_NO_DEVICE / BLIGHT_ERR_CUDA.
+ */
+#ifndef BLIGHT_B200_H
+#define BLIGHT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLIGHT_OK 0
+#define BLIGHT_ERR_INVALID_ARG (-1)  /* std::invalid_argument of the constructor, blight.h:75-92 */
+#define BLIGHT_ERR_IO (-2)           /* std::runtime_error("Problem with files opening"), blight.cpp:188-189 */
+#define BLIGHT_ERR_INVALID_BASE (-3) /* std::domain_error("Invalid char in DNA"), kmer.h:68 */
+#define BLIGHT_ERR_CUDA (-4)
+#define BLIGHT_ERR_NO_DEVICE (-5)
+#define BLIGHT_ERR_FORMAT (-6)
+#define BLIGHT_ERR_NOMEM (-7)
+
+typedef struct blight_flat blight_flat;   /* host-side flat index image (BLFLAT01) */
+typedef struct blight_index blight_index; /* device-resident index */
+
+/* Index of the counters written by the read-query entry points. */
+#define BLIGHT_CTR_FOUND 0     /* "Good kmer", TP, blight.cpp:784-785,793 */
+#define BLIGHT_CTR_NOT_FOUND 1 /* "Erroneous kmers", FP, blight.cpp:786-787,794 */
+#define BLIGHT_CTR_QUERIES 2   /* number_query, blight.cpp:687-688,795 */
+#define BLIGHT_CTR_INVALID 3   /* bytes that nuc2int would reject (kmer.h:68); non-zero => BLIGHT_ERR_INVALID_BASE */
+#define BLIGHT_N_CTR 4
+
+typedef struct blight_info {
+	uint32_t k, m, n_log2, s_log2, b;
+	uint32_t reserved;
+	uint64_t n_buckets;         /* 2^(2m-1), blight.h:70 */
+	uint64_t n_mphf;            /* 2^n, blight.h:68 */
+	uint64_t number_kmer;       /* kmer_Set_Light::number_kmer, blight.h:52 */
+	uint64_t number_super_kmer; /* kmer_Set_Light::number_super_kmer, blight.h:53 */
+	uint64_t total_nuc;         /* bucketSeq.size()/2 */
+	uint64_t positions_bits;    /* positions.size() */
+	uint64_t mphf_bits;         /* sum of the BBHash level bit arrays */
+	uint64_t fallback_keys;     /* entries of the BBHash fallback maps */
+	uint64_t largest_mphf;      /* kmer_Set_Light::largest_MPHF, blight.h:54 */
+	uint64_t largest_bucket;    /* kmer_Set_Light::largest_bucket_nuc_all, blight.h:59 */
+	uint64_t device_bytes;      /* HBM bytes held by a blight_index (0 for a blight_flat) */
+} blight_info;
+
+const char* blight_version(void);
+/* Message of the last error raised on the calling thread ("" if none). */
+const char* blight_last_error(void);
+
+/* ---- host side: construction and (de)serialisation of the flat index ---------------------------------- */
+
+/* kmer_Set_Light(k,m,n,s,cores,b) parameter validation, blight.h:62-96. */
+int blight_check_params(uint32_t k, uint32_t m, uint32_t n_log2, uint32_t s_log2, uint32_t b);
+
+/* kmer_Set_Light::construct_index(file), blight.h:134 / blight.cpp:108-125: builds, on the host, bit for bit the
+ * index the reference builds with cores=1 (2-line FASTA records, plain or gzip). `threads` is ours (0 = all). */
+int blight_flat_build_file(const char* unitig_path, uint32_t k, uint32_t m, uint32_t n_log2, uint32_t s_log2, uint32_t b,
+                           uint32_t threads, blight_flat** out);
+/* Same, from sequences already in memory: sequence i = bases[offsets[i] .. offsets[i+1]). */
+int blight_flat_build_seqs(const char* bases, const uint64_t* offsets, uint64_t n_seqs, uint32_t k, uint32_t m,
+                           uint32_t n_log2, uint32_t s_log2, uint32_t b, uint32_t threads, blight_flat** out);
+/* The reference has no index persistence (only mphf::save/load, bbhash.h:731-775); this is ours. */
+int blight_flat_save(const blight_flat* f, const char* path);
+int blight_flat_load(const char* path, blight_flat** out);
+void blight_flat_free(blight_flat* f);
+int blight_flat_info(const blight_flat* f, blight_info* out);
+/* 0 if a and b hold identical indices, 1 if they differ (description via blight_last_error), <0 on error. */
+int blight_flat_compare(const blight_flat* a, const blight_flat* b);
+/* Keeps only MPHF groups [g_begin, g_end) (minimizer-bucket partition for multi-GPU); ids stay global. */
+int blight_flat_slice(const blight_flat* f, uint64_t g_begin, uint64_t g_end, blight_flat** out);
+/* k-mer count of every MPHF group (n_mphf entries), for balancing a partition. */
+int blight_flat_group_sizes(const blight_flat* f, uint64_t* sizes_out);
+
+/* ---- device side ------------------------------------------------------------------------------------ */
+
+/* Re-lays the flat image out for the GPU and uploads it to `device`. */
+int blight_index_upload(const blight_flat* f, int device, blight_index** out);
+void blight_index_free(blight_index* idx);
+int blight_index_info(const blight_index* idx, blight_info* out);
+
+/* kmer_Set_Light::query_kmer_hash(canon), blight.h:131 / blight.cpp:545-550, batched: d_canon[i] must already be
+ * canonical; d_ids[i] = identifier in [0, N) or -1. */
+int blight_query_kmers(const blight_index* idx, const uint64_t* d_canon, uint64_t n, int64_t* d_ids, void* stream);
+
+/* Same with the minimizer bucket supplied by the caller (query_get_hash(canon, minimizer), blight.cpp:716-742);
+ * used by the bucket-partitioned multi-GPU path, where the owner receives (canon, minimizer) pairs. */
+int blight_query_kmers_mini(const blight_index* idx, const uint64_t* d_canon, const uint32_t* d_mini, uint64_t n,
+                            int64_t* d_ids, void* stream);
+
+/* Front end only: canonical k-mers and minimizers of every k-mer of every read, in read order then position
+ * (query_sequence_hash's order, blight.cpp:575-591; minimizer_naive, kmer.h:791-810). Read r is
+ * d_bases[d_read_off[r] .. d_read_off[r+1]); its k-mers land at d_kmer_off[r].. (d_kmer_off = exclusive prefix of
+ * max(0, len-k+1), n_reads+1 entries). d_ctr[BLIGHT_CTR_INVALID] counts rejected bytes. Needs no index: pass k, m. */
+int blight_reads_to_kmers(uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
+                          const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, uint64_t* d_canon,
+                          uint32_t* d_mini, uint64_t* d_ctr, void* stream);
+
+/* kmer_Set_Light::query_sequence_hash / query_sequence_bool over a batch of reads (blight.h:129,133), the body of
+ * file_query's loop (blight.cpp:780-789). d_ids may be NULL (bool mode: only counters). d_ctr has BLIGHT_N_CTR
+ * entries and is ACCUMULATED into (zero it first). Reads shorter than k contribute nothing (blight.cpp:557-559). */
+int blight_query_reads(const blight_index* idx, const char* d_bases, const uint64_t* d_read_off,
+                       const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, uint64_t total_kmers,
+                       int64_t* d_ids, uint64_t* d_ctr, void* stream);
+
+/* ---- host-buffer entry points (end to end: H2D, kernels, D2H inside the call) ------------------------- */
+
+/* kmer_Set_Light::file_query on a text buffer holding 2-line FASTA records (blight.cpp:746-799): same record
+ * pairing, same skip rule; ctr[BLIGHT_N_CTR] receives Good / Erroneous / Query performed / invalid bytes. */
+int blight_query_fasta_host(const blight_index* idx, const char* text, uint64_t len, uint64_t* ctr);
+/* file_query(path): plain or gzip file. */
+int blight_query_file_host(const blight_index* idx, const char* path, uint64_t* ctr);
+/* query_sequence_hash(seq): ids_out needs max(0, len-k+1) slots; *n_out receives the count. */
+int blight_query_sequence_host(const blight_index* idx, const char* seq, uint64_t len, int64_t* ids_out,
+                               uint64_t* n_out);
+/* Batched form over host reads (no separators; offsets as above); ids_out may be NULL. */
+int blight_query_reads_host(const blight_index* idx, const char* bases, const uint64_t* read_off, uint64_t n_reads,
+                            int64_t* ids_out, uint64_t* ctr);
+/* query_kmer_hash over a host array of canonical k-mers. */
+int blight_query_kmers_host(const blight_index* idx, const uint64_t* canon, uint64_t n, int64_t* ids_out);
+
+/* Number of kernel launches issued by this library in the calling process (all threads) since load. */
+uint64_t blight_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLIGHT_B200_H */
