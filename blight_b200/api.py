@@ -1,0 +1,353 @@
+"""ctypes binding of the C ABI (include/blight_b200.h) and a Python mirror of the reference's
+`kmer_Set_Light` surface (blight.h:15-136) on top of it.
+
+PyTorch is only plumbing here: device buffers, streams, torch.distributed.  Every query goes through the
+in-tree CUDA library; if it is missing or no GPU is present the calls fail loudly (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libblight_b200.so")
+
+OK = 0
+ERR_INVALID_ARG, ERR_IO, ERR_INVALID_BASE, ERR_CUDA, ERR_NO_DEVICE, ERR_FORMAT, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
+CTR_FOUND, CTR_NOT_FOUND, CTR_QUERIES, CTR_INVALID, N_CTR = 0, 1, 2, 3, 4
+
+# every symbol include/blight_b200.h declares
+SYMBOLS = [
+    "blight_version", "blight_last_error", "blight_check_params", "blight_flat_build_file", "blight_flat_build_seqs", "blight_flat_build_spans",
+    "blight_flat_save", "blight_flat_load", "blight_flat_free", "blight_flat_info", "blight_flat_compare",
+    "blight_flat_slice", "blight_flat_group_sizes", "blight_index_upload", "blight_index_free", "blight_index_info",
+    "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads",
+    "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
+    "blight_query_kmers_host", "blight_launch_count",
+]
+
+
+class BlightError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"blight_b200 error {code}: {msg}")
+        self.code = code
+
+
+class InvalidBase(BlightError, ValueError):
+    """std::domain_error("Invalid char in DNA") of the reference (kmer.h:68)."""
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("k", "m", "n_log2", "s_log2", "b", "reserved")] + [
+        (n, C.c_uint64) for n in ("n_buckets", "n_mphf", "number_kmer", "number_super_kmer", "total_nuc", "positions_bits",
+                                  "mphf_bits", "fallback_keys", "largest_mphf", "largest_bucket", "device_bytes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the in-tree shared library (built by __graft_entry__.build() / make -C blight_b200/csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(blight_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, cp = C.c_void_p, C.c_uint32, C.c_uint64, C.c_char_p
+    L.blight_version.restype = cp
+    L.blight_last_error.restype = cp
+    L.blight_check_params.argtypes = [u32] * 5
+    L.blight_flat_build_file.argtypes = [cp] + [u32] * 6 + [C.POINTER(vp)]
+    L.blight_flat_build_seqs.argtypes = [vp, vp, u64] + [u32] * 6 + [C.POINTER(vp)]
+    L.blight_flat_build_spans.argtypes = [vp, vp, vp, u64] + [u32] * 6 + [C.POINTER(vp)]
+    L.blight_flat_save.argtypes = [vp, cp]
+    L.blight_flat_load.argtypes = [cp, C.POINTER(vp)]
+    L.blight_flat_free.argtypes = [vp]
+    L.blight_flat_free.restype = None
+    L.blight_flat_info.argtypes = [vp, C.POINTER(Info)]
+    L.blight_flat_compare.argtypes = [vp, vp]
+    L.blight_flat_slice.argtypes = [vp, u64, u64, C.POINTER(vp)]
+    L.blight_flat_group_sizes.argtypes = [vp, vp]
+    L.blight_index_upload.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.blight_index_free.argtypes = [vp]
+    L.blight_index_free.restype = None
+    L.blight_index_info.argtypes = [vp, C.POINTER(Info)]
+    L.blight_query_kmers.argtypes = [vp, vp, u64, vp, vp]
+    L.blight_query_kmers_mini.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.blight_reads_to_kmers.argtypes = [u32, u32, vp, vp, vp, u64, u64, vp, vp, vp, vp]
+    L.blight_query_reads.argtypes = [vp, vp, vp, vp, u64, u64, u64, vp, vp, vp]
+    L.blight_query_fasta_host.argtypes = [vp, vp, u64, vp]
+    L.blight_query_file_host.argtypes = [vp, cp, vp]
+    L.blight_query_sequence_host.argtypes = [vp, vp, u64, vp, C.POINTER(u64)]
+    L.blight_query_reads_host.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.blight_query_kmers_host.argtypes = [vp, vp, u64, vp]
+    L.blight_launch_count.restype = u64
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc == OK:
+        return
+    msg = lib().blight_last_error().decode(errors="replace")
+    if rc == ERR_INVALID_BASE:
+        raise InvalidBase(rc, msg)
+    raise BlightError(rc, msg)
+
+
+def launch_count() -> int:
+    return int(lib().blight_launch_count())
+
+
+class FlatIndex:
+    """Host-side flat index image (BLFLAT01)."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def build_file(cls, path: str, k=31, m=9, n=17, s=6, b=6, threads=0) -> "FlatIndex":
+        h = C.c_void_p()
+        _check(lib().blight_flat_build_file(os.fsencode(path), k, m, n, s, b, threads, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build_seqs(cls, bases: np.ndarray, offsets: np.ndarray, k=31, m=9, n=17, s=6, b=6, threads=0) -> "FlatIndex":
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(lib().blight_flat_build_seqs(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k, m, n, s, b,
+                                            threads, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build_spans(cls, bases: np.ndarray, starts: np.ndarray, lengths: np.ndarray, k=31, m=9, n=17, s=6, b=6, threads=0) -> "FlatIndex":
+        """Sequences are (possibly overlapping) spans of one base buffer: bases[starts[i] : starts[i]+lengths[i]]."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(lib().blight_flat_build_spans(bases.ctypes.data, starts.ctypes.data, lengths.ctypes.data, len(starts),
+                                             k, m, n, s, b, threads, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def load(cls, path: str) -> "FlatIndex":
+        h = C.c_void_p()
+        _check(lib().blight_flat_load(os.fsencode(path), C.byref(h)))
+        return cls(h.value)
+
+    def save(self, path: str):
+        _check(lib().blight_flat_save(self._h, os.fsencode(path)))
+
+    def info(self) -> dict:
+        i = Info()
+        _check(lib().blight_flat_info(self._h, C.byref(i)))
+        return i.as_dict()
+
+    def equals(self, other: "FlatIndex") -> bool:
+        rc = lib().blight_flat_compare(self._h, other._h)
+        if rc < 0:
+            _check(rc)
+        return rc == 0
+
+    def difference(self, other: "FlatIndex") -> str:
+        rc = lib().blight_flat_compare(self._h, other._h)
+        return "" if rc == 0 else lib().blight_last_error().decode()
+
+    def group_sizes(self) -> np.ndarray:
+        out = np.zeros(self.info()["n_mphf"], dtype=np.uint64)
+        _check(lib().blight_flat_group_sizes(self._h, out.ctypes.data))
+        return out
+
+    def slice(self, g_begin: int, g_end: int) -> "FlatIndex":
+        h = C.c_void_p()
+        _check(lib().blight_flat_slice(self._h, g_begin, g_end, C.byref(h)))
+        return FlatIndex(h.value)
+
+    def upload(self, device: int = 0) -> "DeviceIndex":
+        h = C.c_void_p()
+        _check(lib().blight_index_upload(self._h, device, C.byref(h)))
+        return DeviceIndex(h.value, device)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.blight_flat_free(self._h)
+            self._h = C.c_void_p()
+
+
+def _ptr(t) -> int:
+    """data pointer of a torch tensor / numpy array / None"""
+    if t is None:
+        return 0
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def _stream_handle(stream) -> int:
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+class DeviceIndex:
+    """Index resident in HBM. Device-buffer methods take torch CUDA tensors and are asynchronous on the given
+    (default: torch's current) stream; *_host methods take numpy / bytes and are synchronous."""
+
+    def __init__(self, handle: int, device: int):
+        self._h = C.c_void_p(handle)
+        self.device = device
+        i = Info()
+        _check(lib().blight_index_info(self._h, C.byref(i)))
+        self.info = i.as_dict()
+        self.k = self.info["k"]
+        self.m = self.info["m"]
+
+    # -- device buffers ----------------------------------------------------------------------------------
+    def query_kmers(self, canon, out=None, mini=None, stream=None):
+        import torch
+        assert canon.is_cuda and canon.dtype in (torch.int64, torch.uint64) and canon.is_contiguous()
+        n = canon.numel()
+        if out is None:
+            out = torch.empty(n, dtype=torch.int64, device=canon.device)
+        if mini is None:
+            _check(lib().blight_query_kmers(self._h, _ptr(canon), n, _ptr(out), _stream_handle(stream)))
+        else:
+            assert mini.is_cuda and mini.numel() == n and mini.element_size() == 4 and mini.is_contiguous()
+            _check(lib().blight_query_kmers_mini(self._h, _ptr(canon), _ptr(mini), n, _ptr(out), _stream_handle(stream)))
+        return out
+
+    def query_reads(self, bases, read_off, kmer_off=None, total_kmers=0, ids=None, ctr=None, want_ids=True, stream=None):
+        """bases: uint8 CUDA tensor; read_off: int64/uint64 CUDA tensor (n+1); returns (ids or None, ctr[4])."""
+        import torch
+        n_reads = read_off.numel() - 1
+        if ctr is None:
+            ctr = torch.zeros(N_CTR, dtype=torch.int64, device=bases.device)
+        if want_ids and ids is None:
+            ids = torch.empty(max(int(total_kmers), 1), dtype=torch.int64, device=bases.device)
+        _check(lib().blight_query_reads(self._h, _ptr(bases), _ptr(read_off), _ptr(kmer_off), n_reads, bases.numel(),
+                                        int(total_kmers), _ptr(ids) if want_ids else 0, _ptr(ctr), _stream_handle(stream)))
+        return (ids if want_ids else None), ctr
+
+    # -- host buffers ------------------------------------------------------------------------------------
+    def query_fasta_host(self, text) -> np.ndarray:
+        """file_query on a text buffer -> [found, not_found, queries, invalid]"""
+        ctr = np.zeros(N_CTR, dtype=np.uint64)
+        if isinstance(text, (bytes, bytearray)):
+            buf = np.frombuffer(text, dtype=np.uint8)
+        else:
+            buf = text
+        _check(lib().blight_query_fasta_host(self._h, _ptr(buf), len(buf) if isinstance(buf, np.ndarray) else buf.numel(), ctr.ctypes.data))
+        return ctr
+
+    def query_file_host(self, path: str) -> np.ndarray:
+        ctr = np.zeros(N_CTR, dtype=np.uint64)
+        _check(lib().blight_query_file_host(self._h, os.fsencode(path), ctr.ctypes.data))
+        return ctr
+
+    def query_sequence_host(self, seq) -> np.ndarray:
+        if isinstance(seq, str):
+            seq = seq.encode()
+        buf = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        out = np.empty(max(len(buf) - self.k + 1, 0), dtype=np.int64)
+        n = C.c_uint64()
+        _check(lib().blight_query_sequence_host(self._h, buf.ctypes.data, len(buf), out.ctypes.data, C.byref(n)))
+        return out[:n.value]
+
+    def query_reads_host(self, bases: np.ndarray, read_off: np.ndarray, want_ids=True):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        n = len(read_off) - 1
+        ids = None
+        if want_ids:
+            lens = np.diff(read_off.astype(np.int64))
+            ids = np.empty(int(np.maximum(lens - (self.k - 1), 0).sum()), dtype=np.int64)
+        ctr = np.zeros(N_CTR, dtype=np.uint64)
+        _check(lib().blight_query_reads_host(self._h, bases.ctypes.data, read_off.ctypes.data, n, _ptr(ids), ctr.ctypes.data))
+        return ids, ctr
+
+    def query_kmers_host(self, canon: np.ndarray) -> np.ndarray:
+        canon = np.ascontiguousarray(canon, dtype=np.uint64)
+        out = np.empty(len(canon), dtype=np.int64)
+        _check(lib().blight_query_kmers_host(self._h, canon.ctypes.data, len(canon), out.ctypes.data))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.blight_index_free(self._h)
+            self._h = C.c_void_p()
+
+
+def reads_to_kmers(k: int, m: int, bases, read_off, kmer_off, total_kmers: int, stream=None):
+    """Front end only: (canon uint64-as-int64, minimizer int32, ctr) for every k-mer of every read."""
+    import torch
+    canon = torch.empty(max(total_kmers, 1), dtype=torch.int64, device=bases.device)
+    mini = torch.empty(max(total_kmers, 1), dtype=torch.int32, device=bases.device)
+    ctr = torch.zeros(N_CTR, dtype=torch.int64, device=bases.device)
+    _check(lib().blight_reads_to_kmers(k, m, _ptr(bases), _ptr(read_off), _ptr(kmer_off), read_off.numel() - 1,
+                                       bases.numel(), _ptr(canon), _ptr(mini), _ptr(ctr), _stream_handle(stream)))
+    return canon[:total_kmers], mini[:total_kmers], ctr
+
+
+class KmerSetLight:
+    """Python mirror of `kmer_Set_Light` (blight.h:15-136): same constructor arguments, `construct_index`,
+    `file_query`, `query_sequence_bool`, `query_sequence_hash`, `query_kmer_bool`, `query_kmer_hash`, and the public
+    counters `number_kmer`, `number_super_kmer`, `number_query`."""
+
+    def __init__(self, k: int, m: int, log2_mphfs: int, log2_superbuckets: int, cores: int, bits_to_save: int, device: int = 0):
+        rc = lib().blight_check_params(k, m, log2_mphfs, log2_superbuckets, bits_to_save)
+        if rc != OK:
+            raise ValueError(lib().blight_last_error().decode())  # std::invalid_argument (blight.h:75-92)
+        self.k, self.m, self.n, self.s, self.cores, self.b, self.device = k, m, log2_mphfs, log2_superbuckets, cores, bits_to_save, device
+        self.flat: Optional[FlatIndex] = None
+        self.index: Optional[DeviceIndex] = None
+        self.number_kmer = 0
+        self.number_super_kmer = 0
+        self.number_query = 0
+
+    def construct_index(self, input_file: str):
+        self.flat = FlatIndex.build_file(input_file, self.k, self.m, self.n, self.s, self.b, self.cores)
+        self._after_build()
+
+    def import_flat(self, flat: FlatIndex):
+        """Adopts an index built elsewhere (e.g. exported from the reference's own construction)."""
+        self.flat = flat
+        self._after_build()
+
+    def _after_build(self):
+        i = self.flat.info()
+        self.number_kmer, self.number_super_kmer = i["number_kmer"], i["number_super_kmer"]
+        self.index = self.flat.upload(self.device)
+
+    def file_query(self, query_file: str):
+        ctr = self.index.query_file_host(query_file)
+        self.number_query += int(ctr[CTR_QUERIES])
+        return int(ctr[CTR_FOUND]), int(ctr[CTR_NOT_FOUND])
+
+    def query_sequence_hash(self, query: str) -> np.ndarray:
+        ids = self.index.query_sequence_host(query)
+        self.number_query += len(ids)
+        return ids
+
+    def query_sequence_bool(self, query: str):
+        ids = self.query_sequence_hash(query)
+        return int((ids >= 0).sum()), int((ids < 0).sum())
+
+    def query_kmer_hash(self, canon: int) -> int:
+        self.number_query += 1
+        return int(self.index.query_kmers_host(np.array([canon], dtype=np.uint64))[0])
+
+    def query_kmer_bool(self, canon: int) -> bool:
+        return self.query_kmer_hash(canon) >= 0

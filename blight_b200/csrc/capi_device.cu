@@ -1,0 +1,373 @@
+// capi_device.cu — the device half of the C ABI (include/blight_b200.h): re-layout + upload of the flat index,
+// device-buffer query entry points, and the host-buffer (end to end) entry points.
+#include <cuda_runtime.h>
+#include <omp.h>
+
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "capi_common.hpp"
+#include "device_index.hpp"
+#include "kernels.hpp"
+#include "kmer_math.hpp"
+
+using namespace blight;
+
+namespace {
+
+int cuda_fail(cudaError_t e, const char* what) {
+	return fail(BL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                          \
+	do {                                                  \
+		cudaError_t e__ = (call);                         \
+		if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+	} while (0)
+
+struct DeviceGuard {
+	int prev = -1;
+	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+	~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <class T>
+int upload(const std::vector<T>& v, void** d, uint64_t* bytes_acc) {
+	const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 256);
+	CU(cudaMalloc(d, bytes));
+	CU(cudaMemset(*d, 0, bytes));
+	if (!v.empty()) CU(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+	*bytes_acc += bytes;
+	return BL_OK;
+}
+
+int ensure_device(int device) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) return fail(BL_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+	if (device < 0 || device >= n) return fail(BL_ERR_INVALID_ARG, "device ordinal out of range");
+	return BL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
+	if (!ff || !out) return fail(BL_ERR_INVALID_ARG, "null argument");
+	int rc = ensure_device(device);
+	if (rc != BL_OK) return rc;
+	const FlatIndex& F = ff->f;
+	const FlatHeader& H = F.h;
+	std::string err;
+	rc = flat_validate(F, &err);
+	if (rc != BL_OK) return fail(rc, err);
+	for (const MphfRec& r : F.mphf)
+		if (r.nelem >= (1ull << 32)) return fail(BL_ERR_INVALID_ARG, "an MPHF group holds 2^32 or more k-mers; use a larger n");
+
+	// ---- re-layout on the host ----
+	std::vector<uint4> bucket(H.n_buckets);
+	for (uint64_t i = 0; i < H.n_buckets; i++)
+		bucket[i] = make_uint4((uint32_t)F.bucket_start[i], (uint32_t)(F.bucket_start[i] >> 32), F.bucket_nuc[i], 0u);
+
+	std::vector<DevMphf> mphf(H.n_mphf);
+	uint64_t bits_sectors = 0, pos_sectors = 0;
+	for (uint64_t g = 0; g < H.n_mphf; g++) {
+		const MphfRec& r = F.mphf[g];
+		DevMphf& d = mphf[g];
+		std::memset(&d, 0, sizeof d);
+		d.bits_sector_base = bits_sectors;
+		d.pos_sector_base = pos_sectors;
+		d.id_offset = r.id_offset;
+		d.fb_off = r.fb_off;
+		d.fb_count = (uint32_t)r.fb_count;
+		d.nbits = r.nbits ? r.nbits : 1;
+		d.fields_per_sector = 256 / d.nbits;
+		d.present = r.present;
+		for (int l = 0; l < kLevels; l++) d.dom[l] = r.present ? r.dom[l] : 64;
+		if (r.present) {
+			bits_sectors += (r.bits_nwords * 64 + kChunkBits - 1) / kChunkBits;
+			pos_sectors += (r.nelem + d.fields_per_sector - 1) / d.fields_per_sector;
+		}
+	}
+	std::vector<uint32_t> bits((bits_sectors + 1) * 8, 0), pos((pos_sectors + 1) * 8, 0);
+	#pragma omp parallel for schedule(dynamic, 1)
+	for (uint64_t g = 0; g < H.n_mphf; g++) {
+		const MphfRec& r = F.mphf[g];
+		if (!r.present) continue;
+		const DevMphf& d = mphf[g];
+		// level bits: 224-bit chunks + running popcount
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(F.bits.data() + r.bits_word_off);
+		const uint64_t n32 = r.bits_nwords * 2;
+		const uint64_t chunks = (r.bits_nwords * 64 + kChunkBits - 1) / kChunkBits;
+		uint32_t ones = 0;
+		uint32_t* dst = bits.data() + d.bits_sector_base * 8;
+		for (uint64_t c = 0; c < chunks; c++, dst += 8) {
+			dst[7] = ones;
+			for (int j = 0; j < 7; j++) {
+				const uint64_t si = c * 7 + j;
+				const uint32_t wv = si < n32 ? src[si] : 0u;
+				dst[j] = wv;
+				ones += (uint32_t)popc32(wv);
+			}
+		}
+		// positions: fields_per_sector fields per 32-byte sector, LSB-first inside the sector
+		uint32_t* pd = pos.data() + d.pos_sector_base * 8;
+		const uint32_t nb = d.nbits, fps = d.fields_per_sector;
+		for (uint64_t rk = 0; rk < r.nelem; rk++) {
+			const uint64_t bitpos = r.pos_start + rk * nb;
+			const uint64_t w0 = F.pos[bitpos >> 6];
+			const uint64_t w1 = ((bitpos >> 6) + 1 < F.pos.size()) ? F.pos[(bitpos >> 6) + 1] : 0;
+			const unsigned sh = unsigned(bitpos & 63);
+			uint64_t v = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
+			v &= (nb >= 64) ? ~0ull : ((1ull << nb) - 1);
+			const uint64_t sec = rk / fps;
+			const uint32_t o = uint32_t(rk % fps) * nb;
+			uint32_t* sp = pd + sec * 8;
+			sp[o >> 5] |= uint32_t(v << (o & 31));
+			if ((o & 31) + nb > 32) sp[(o >> 5) + 1] |= uint32_t(v >> (32 - (o & 31)));
+		}
+	}
+	// sequences: bit reversal of each 32-bit group turns the vector<bool> image (nucleotide p at bits 2p,2p+1 with the
+	// code's high bit first) into 16 codes per word, first base in the high bits
+	const uint64_t seq_pad = ((1ull << H.b) + H.k) / 16 + 8;
+	std::vector<uint32_t> seq(H.seq_words * 2 + seq_pad, 0);
+	{
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(F.seq.data());
+		const int64_t n32 = (int64_t)H.seq_words * 2;
+		#pragma omp parallel for schedule(static)
+		for (int64_t i = 0; i < n32; i++) seq[i] = bitrev32(src[i]);
+	}
+
+	// ---- upload ----
+	DeviceGuard guard(device);
+	blight_index* idx = new blight_index();
+	idx->device = device;
+	uint64_t bytes = 0;
+	rc = upload(bucket, &idx->d_bucket, &bytes);
+	if (rc == BL_OK) rc = upload(mphf, &idx->d_mphf, &bytes);
+	if (rc == BL_OK) rc = upload(bits, &idx->d_bits, &bytes);
+	if (rc == BL_OK) rc = upload(pos, &idx->d_pos, &bytes);
+	if (rc == BL_OK) rc = upload(seq, &idx->d_seq, &bytes);
+	if (rc == BL_OK) rc = upload(F.fb_keys, &idx->d_fbk, &bytes);
+	if (rc == BL_OK) rc = upload(F.fb_vals, &idx->d_fbv, &bytes);
+	if (rc != BL_OK) { blight_index_free(idx); return rc; }
+	cudaStream_t st;
+	cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+	if (e != cudaSuccess) { blight_index_free(idx); return cuda_fail(e, "cudaStreamCreate"); }
+	idx->host_stream = st;
+	idx->host_mutex = new std::mutex();
+	DevIndexView& v = idx->v;
+	v.bucket = static_cast<const uint4*>(idx->d_bucket);
+	v.mphf = static_cast<const DevMphf*>(idx->d_mphf);
+	v.bits = static_cast<const uint32_t*>(idx->d_bits);
+	v.pos = static_cast<const uint32_t*>(idx->d_pos);
+	v.seq = static_cast<const uint32_t*>(idx->d_seq);
+	v.fb_keys = static_cast<const uint64_t*>(idx->d_fbk);
+	v.fb_vals = static_cast<const uint64_t*>(idx->d_fbv);
+	v.k = H.k; v.m = H.m; v.b = H.b; v.lb = F.lb();
+	v.kmask = (1ull << (2 * H.k)) - 1;
+	fill_info(F, &idx->info);
+	idx->info.device_bytes = bytes;
+	*out = idx;
+	return BL_OK;
+}
+
+void blight_index_free(blight_index* idx) {
+	if (!idx) return;
+	DeviceGuard guard(idx->device);
+	cudaFree(idx->d_bucket); cudaFree(idx->d_mphf); cudaFree(idx->d_bits); cudaFree(idx->d_pos); cudaFree(idx->d_seq);
+	cudaFree(idx->d_fbk); cudaFree(idx->d_fbv);
+	for (void* w : idx->ws) cudaFree(w);
+	if (idx->host_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->host_stream));
+	delete static_cast<std::mutex*>(idx->host_mutex);
+	delete idx;
+}
+
+int blight_index_info(const blight_index* idx, blight_info* out) {
+	if (!idx || !out) return fail(BL_ERR_INVALID_ARG, "null argument");
+	*out = idx->info;
+	return BL_OK;
+}
+
+// ---- device-buffer entry points ---------------------------------------------------------------------------
+
+int blight_query_kmers(const blight_index* idx, const uint64_t* d_canon, uint64_t n, int64_t* d_ids, void* stream) {
+	if (!idx || (n && (!d_canon || !d_ids))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	DeviceGuard guard(idx->device);
+	int rc = launch_lookup_kmers(idx->v, d_canon, nullptr, n, d_ids, static_cast<cudaStream_t>(stream));
+	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+}
+
+int blight_query_kmers_mini(const blight_index* idx, const uint64_t* d_canon, const uint32_t* d_mini, uint64_t n,
+                            int64_t* d_ids, void* stream) {
+	if (!idx || (n && (!d_canon || !d_mini || !d_ids))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	DeviceGuard guard(idx->device);
+	int rc = launch_lookup_kmers(idx->v, d_canon, d_mini, n, d_ids, static_cast<cudaStream_t>(stream));
+	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+}
+
+int blight_reads_to_kmers(uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
+                          const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, uint64_t* d_canon,
+                          uint32_t* d_mini, uint64_t* d_ctr, void* stream) {
+	if (n_reads && (!d_bases || !d_read_off || !d_kmer_off || !d_canon || !d_mini || !d_ctr)) return fail(BL_ERR_INVALID_ARG, "null argument");
+	BuildParams p; p.k = k; p.m = m; p.n_log2 = 0; p.s_log2 = 0; p.b = 0;
+	std::string err;
+	int rc = check_params(p, &err);
+	if (rc != BL_OK) return fail(rc, err);
+	rc = launch_reads(nullptr, k, m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, d_canon, d_mini, nullptr, d_ctr,
+	                  static_cast<cudaStream_t>(stream));
+	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+}
+
+int blight_query_reads(const blight_index* idx, const char* d_bases, const uint64_t* d_read_off,
+                       const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, uint64_t total_kmers,
+                       int64_t* d_ids, uint64_t* d_ctr, void* stream) {
+	(void)total_kmers;
+	if (!idx || (n_reads && (!d_bases || !d_read_off || !d_ctr || (d_ids && !d_kmer_off)))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	DeviceGuard guard(idx->device);
+	int rc = launch_reads(&idx->v, idx->v.k, idx->v.m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, nullptr, nullptr,
+	                      d_ids, d_ctr, static_cast<cudaStream_t>(stream));
+	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+}
+
+// ---- host-buffer entry points -----------------------------------------------------------------------------
+
+namespace {
+
+// Grow-only device scratch of the host-buffer entry points (guarded by the index's host mutex).
+int ws_reserve(const blight_index* idx, int slot, size_t bytes, void** out) {
+	blight_index* m = const_cast<blight_index*>(idx);
+	if (m->ws_cap[slot] < bytes) {
+		if (m->ws[slot]) cudaFree(m->ws[slot]);
+		m->ws[slot] = nullptr; m->ws_cap[slot] = 0;
+		const size_t cap = bytes + bytes / 8 + 4096;
+		cudaError_t e = cudaMalloc(&m->ws[slot], cap);
+		if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+		m->ws_cap[slot] = cap;
+	}
+	*out = m->ws[slot];
+	return BL_OK;
+}
+
+// Runs the reads kernel on a host buffer whose reads are [beg[i], end[i]) (beg has n+1 entries; end == null means
+// end[i] = beg[i+1]). H2D of the buffer and the offsets, one kernel, D2H of counters (and ids) — all on the
+// index's internal stream, inside this call.
+int run_host_reads(const blight_index* idx, const char* text, uint64_t len, const uint64_t* beg, const uint64_t* end,
+                   uint64_t n, const uint64_t* koff, int64_t* ids_out, uint64_t total_kmers, uint64_t* ctr) {
+	std::memset(ctr, 0, sizeof(uint64_t) * BLIGHT_N_CTR);
+	if (n == 0 || len == 0) return BL_OK;
+	DeviceGuard guard(idx->device);
+	std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(idx->host_mutex));
+	cudaStream_t st = static_cast<cudaStream_t>(idx->host_stream);
+	void *d_text = nullptr, *d_beg = nullptr, *d_end = nullptr, *d_koff = nullptr, *d_ctr = nullptr, *d_ids = nullptr;
+	int rc;
+	if ((rc = ws_reserve(idx, 0, len + 64, &d_text)) != BL_OK) return rc;
+	if ((rc = ws_reserve(idx, 1, (n + 1) * 8, &d_beg)) != BL_OK) return rc;
+	if (end && (rc = ws_reserve(idx, 2, n * 8, &d_end)) != BL_OK) return rc;
+	if ((rc = ws_reserve(idx, 3, BLIGHT_N_CTR * 8, &d_ctr)) != BL_OK) return rc;
+	if (ids_out) {
+		if ((rc = ws_reserve(idx, 4, (n + 1) * 8, &d_koff)) != BL_OK) return rc;
+		if ((rc = ws_reserve(idx, 5, std::max<uint64_t>(total_kmers, 1) * 8, &d_ids)) != BL_OK) return rc;
+	}
+	CU(cudaMemcpyAsync(d_text, text, len, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(d_beg, beg, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	if (end) CU(cudaMemcpyAsync(d_end, end, n * 8, cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(d_ctr, 0, BLIGHT_N_CTR * 8, st));
+	if (ids_out) CU(cudaMemcpyAsync(d_koff, koff, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	rc = launch_reads(&idx->v, idx->v.k, idx->v.m, static_cast<const char*>(d_text), static_cast<const uint64_t*>(d_beg),
+	                  static_cast<const uint64_t*>(end ? d_end : nullptr), static_cast<const uint64_t*>(d_koff), n, len, nullptr,
+	                  nullptr, static_cast<int64_t*>(d_ids), static_cast<uint64_t*>(d_ctr), st);
+	if (rc != BL_OK) return fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+	if (ids_out && total_kmers) CU(cudaMemcpyAsync(ids_out, d_ids, total_kmers * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(ctr, d_ctr, BLIGHT_N_CTR * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (ctr[BLIGHT_CTR_INVALID]) return fail(BL_ERR_INVALID_BASE, "Invalid char in DNA");
+	return BL_OK;
+}
+
+}  // namespace
+
+int blight_query_fasta_host(const blight_index* idx, const char* text, uint64_t len, uint64_t* ctr) {
+	if (!idx || !ctr || (len && !text)) return fail(BL_ERR_INVALID_ARG, "null argument");
+	std::vector<SeqView> recs;
+	split_fasta_records(text, len, recs);
+	std::vector<uint64_t> beg(recs.size() + 1), end(recs.size());
+	for (size_t i = 0; i < recs.size(); i++) { beg[i] = uint64_t(recs[i].p - text); end[i] = beg[i] + recs[i].len; }
+	beg[recs.size()] = len;
+	return run_host_reads(idx, text, len, beg.data(), end.data(), end.size(), nullptr, nullptr, 0, ctr);
+}
+
+int blight_query_file_host(const blight_index* idx, const char* path, uint64_t* ctr) {
+	if (!idx || !ctr || !path) return fail(BL_ERR_INVALID_ARG, "null argument");
+	std::string storage, err;
+	std::vector<SeqView> recs;
+	int rc = read_fasta_records(path, storage, recs, &err);
+	if (rc != BL_OK) return fail(rc, err);
+	std::vector<uint64_t> beg(recs.size() + 1), end(recs.size());
+	for (size_t i = 0; i < recs.size(); i++) { beg[i] = uint64_t(recs[i].p - storage.data()); end[i] = beg[i] + recs[i].len; }
+	beg[recs.size()] = storage.size();
+	return run_host_reads(idx, storage.data(), storage.size(), beg.data(), end.data(), end.size(), nullptr, nullptr, 0, ctr);
+}
+
+int blight_query_reads_host(const blight_index* idx, const char* bases, const uint64_t* read_off, uint64_t n_reads,
+                            int64_t* ids_out, uint64_t* ctr) {
+	if (!idx || !ctr || (n_reads && (!bases || !read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	std::memset(ctr, 0, sizeof(uint64_t) * BLIGHT_N_CTR);
+	if (n_reads == 0) return BL_OK;
+	const uint32_t k = idx->v.k;
+	const uint64_t base0 = read_off[0];
+	std::vector<uint64_t> rebased, koff;
+	const uint64_t* beg = read_off;
+	if (base0 != 0) {
+		rebased.assign(read_off, read_off + n_reads + 1);
+		for (auto& v : rebased) v -= base0;
+		beg = rebased.data();
+	}
+	if (ids_out) {
+		koff.assign(n_reads + 1, 0);
+		for (uint64_t r = 0; r < n_reads; r++) {
+			const uint64_t l = read_off[r + 1] - read_off[r];
+			koff[r + 1] = koff[r] + (l >= k ? l - k + 1 : 0);
+		}
+	}
+	return run_host_reads(idx, bases + base0, read_off[n_reads] - base0, beg, nullptr, n_reads, ids_out ? koff.data() : nullptr, ids_out,
+	                      ids_out ? koff[n_reads] : 0, ctr);
+}
+
+int blight_query_sequence_host(const blight_index* idx, const char* seq, uint64_t len, int64_t* ids_out, uint64_t* n_out) {
+	if (!idx || !n_out || (len && !seq)) return fail(BL_ERR_INVALID_ARG, "null argument");
+	const uint32_t k = idx->v.k;
+	*n_out = len >= k ? len - k + 1 : 0;
+	if (*n_out == 0) return BL_OK;  // query.size() < k: empty result (blight.cpp:577-579)
+	if (!ids_out) return fail(BL_ERR_INVALID_ARG, "null argument");
+	uint64_t off[2] = {0, len}, ctr[BLIGHT_N_CTR];
+	return blight_query_reads_host(idx, seq, off, 1, ids_out, ctr);
+}
+
+int blight_query_kmers_host(const blight_index* idx, const uint64_t* canon, uint64_t n, int64_t* ids_out) {
+	if (!idx || (n && (!canon || !ids_out))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	if (n == 0) return BL_OK;
+	DeviceGuard guard(idx->device);
+	std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(idx->host_mutex));
+	cudaStream_t st = static_cast<cudaStream_t>(idx->host_stream);
+	uint64_t* d_canon = nullptr; int64_t* d_ids = nullptr;
+	cudaError_t e;
+	auto cleanup = [&]() { cudaFree(d_canon); cudaFree(d_ids); };
+#define CUH(call) do { e = (call); if (e != cudaSuccess) { cleanup(); return cuda_fail(e, #call); } } while (0)
+	CUH(cudaMalloc(&d_canon, n * 8));
+	CUH(cudaMalloc(&d_ids, n * 8));
+	CUH(cudaMemcpyAsync(d_canon, canon, n * 8, cudaMemcpyHostToDevice, st));
+	int rc = launch_lookup_kmers(idx->v, d_canon, nullptr, n, d_ids, st);
+	if (rc != BL_OK) { cleanup(); return fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error); }
+	CUH(cudaMemcpyAsync(ids_out, d_ids, n * 8, cudaMemcpyDeviceToHost, st));
+	CUH(cudaStreamSynchronize(st));
+#undef CUH
+	cleanup();
+	return BL_OK;
+}
+
+uint64_t blight_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -38,6 +38,20 @@ int blight_flat_build_seqs(const char* bases, const uint64_t* offsets, uint64_t 
 	return BL_OK;
 }
 
+int blight_flat_build_spans(const char* bases, const uint64_t* starts, const uint64_t* lengths, uint64_t n_seqs, uint32_t k,
+                            uint32_t m, uint32_t n_log2, uint32_t s_log2, uint32_t b, uint32_t threads, blight_flat** out) {
+	if (!out || (n_seqs && (!bases || !starts || !lengths))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	BuildParams p; p.k = k; p.m = m; p.n_log2 = n_log2; p.s_log2 = s_log2; p.b = b; p.threads = threads;
+	std::vector<SeqView> seqs(n_seqs);
+	for (uint64_t i = 0; i < n_seqs; i++) seqs[i] = SeqView{bases + starts[i], lengths[i]};
+	blight_flat* f = new blight_flat();
+	std::string err;
+	int rc = build_flat_index(seqs, p, f->f, &err);
+	if (rc != BL_OK) { delete f; return fail(rc, err); }
+	*out = f;
+	return BL_OK;
+}
+
 int blight_flat_build_file(const char* unitig_path, uint32_t k, uint32_t m, uint32_t n_log2, uint32_t s_log2, uint32_t b,
                            uint32_t threads, blight_flat** out) {
 	if (!out || !unitig_path) return fail(BL_ERR_INVALID_ARG, "null argument");

@@ -1,0 +1,71 @@
+// device_index.hpp — the HBM layout of a Blight index on a B200 and the view kernels receive.
+//
+// The flat image (flat_index.hpp) keeps the reference's bit conventions; the device layout below is ours and is
+// chosen so that every dependent step of a lookup touches exactly one 32-byte sector:
+//
+//   bucket table   one uint4 per minimizer bucket {start_lo, start_hi, nuc, 0}          (blight.h:29-34)
+//   MPHF table     one 256-byte DevMphf per group: sector bases, id offset, positions geometry, dom[16]
+//                                                                                        (blight.h:39-44, bbhash.h:777)
+//   level bits     per group, all 16 BBHash levels back to back, cut into 224-bit chunks; each chunk is stored
+//                  as one 32-byte sector = 7 x u32 of bits + 1 x u32 "ones before this chunk" (group-relative).
+//                  A level probe and the rank that follows (bbhash.h:404-408, 467-480) are ONE sector read
+//                  instead of the reference's bit word + rank sample + up to 15 more words.
+//   positions      per group, fields of `nbits` bits packed floor(256/nbits) to a 32-byte sector, never
+//                  straddling a sector (the reference packs them back to back, blight.cpp:464-482).
+//   sequences      2-bit codes (A0 C1 T2 G3), 16 per u32, FIRST base in the HIGH bits, so a k-mer window is a
+//                  funnel shift of adjacent words (the reference stores one bit per vector<bool> slot,
+//                  blight.cpp:317-318); zero padded past the end for the 2^b-window scan (blight.cpp:732-739).
+//   fallback       sorted (key, rank) arrays for keys no level accommodated (bbhash.h:567-575).
+#pragma once
+#include <cstdint>
+
+#include <vector_types.h>
+
+#include "errors.hpp"
+#include "flat_index.hpp"
+
+namespace blight {
+
+constexpr uint32_t kChunkBits = 224;  // level bits per 32-byte sector
+
+struct alignas(64) DevMphf {
+	uint64_t bits_sector_base;  // first sector of this group's level bits (index into DevIndexView::bits, in sectors)
+	uint64_t pos_sector_base;   // first sector of this group's positions
+	uint64_t id_offset;         // exclusive prefix of k-mer counts: id = rank + id_offset (blight.cpp:736)
+	uint64_t fb_off;            // slice of the fallback arrays
+	uint32_t fb_count;
+	uint32_t nbits;             // position field width
+	uint32_t fields_per_sector; // floor(256 / nbits)
+	uint32_t present;
+	uint64_t pad[2];
+	uint64_t dom[kLevels];      // level domains
+	uint64_t pad2[8];
+};
+static_assert(sizeof(DevMphf) == 256, "DevMphf is 256 bytes");
+
+struct DevIndexView {
+	const uint4* bucket;
+	const DevMphf* mphf;
+	const uint32_t* bits;  // 8 words per sector
+	const uint32_t* pos;   // 8 words per sector
+	const uint32_t* seq;
+	const uint64_t* fb_keys;
+	const uint64_t* fb_vals;
+	uint64_t kmask;
+	uint32_t k, m, b, lb;
+};
+
+}  // namespace blight
+
+// Opaque handle of the C ABI.
+struct blight_index {
+	int device = -1;
+	blight::DevIndexView v{};
+	blight_info info{};
+	void* d_bucket = nullptr; void* d_mphf = nullptr; void* d_bits = nullptr; void* d_pos = nullptr; void* d_seq = nullptr;
+	void* d_fbk = nullptr; void* d_fbv = nullptr;
+	void* host_stream = nullptr;  // internal stream of the *_host entry points
+	void* host_mutex = nullptr;
+	void* ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // grow-only scratch of the *_host entry points
+	size_t ws_cap[6] = {0, 0, 0, 0, 0, 0};
+};

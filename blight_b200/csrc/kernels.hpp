@@ -1,0 +1,30 @@
+// kernels.hpp — launchers of the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+
+#include "device_index.hpp"
+#include "errors.hpp"
+
+namespace blight {
+
+extern std::atomic<uint64_t> g_launches;
+extern const char* g_last_cuda_error;
+
+// ids[i] = lookup(canon[i]); d_mini may be null (the minimizer is then computed from the k-mer).
+int launch_lookup_kmers(const DevIndexView& I, const uint64_t* d_canon, const uint32_t* d_mini, uint64_t n, int64_t* d_ids,
+                        cudaStream_t stream);
+
+// Tile kernel over a base buffer of `total_bases` bytes. Read r starts at d_read_off[r] and ends at d_read_end[r]
+// (or d_read_off[r+1] when d_read_end is null); d_read_off has n_reads+1 ascending entries. The buffer may hold
+// anything between reads (FASTA headers, newlines).
+//   I == null          : front end only, (canon, minimizer) pairs to d_canon / d_mini at d_kmer_off[r] + position
+//   I != null, d_ids   : ids to d_ids at d_kmer_off[r] + position, counters accumulated into d_ctr
+//   I != null, !d_ids  : counters only (d_kmer_off unused, may be null)
+int launch_reads(const DevIndexView* I, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
+                 const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
+                 uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream);
+
+}  // namespace blight

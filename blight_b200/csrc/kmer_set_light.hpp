@@ -1,0 +1,117 @@
+// kmer_set_light.hpp — the drop-in C++ surface: a class with the reference's public query interface
+// (kmer_Set_Light, blight.h:15-136) whose work is done by the sm_100a library behind include/blight_b200.h.
+//
+// Same constructor arguments and exceptions (std::invalid_argument, blight.h:75-92), same method names,
+// argument meaning and results: construct_index (blight.h:134), file_query (:117), query_sequence_bool (:129),
+// query_sequence_hash (:133), query_kmer_bool (:128), query_kmer_hash (:131) and the public counters number_kmer,
+// number_super_kmer, number_query (:52-56).  Non-ACGT input raises std::domain_error like nuc2int (kmer.h:68);
+// an unreadable file raises std::runtime_error (blight.cpp:188-189).  Like the reference object it is
+// non-copyable; queries may be issued concurrently from several host threads.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "blight_b200.h"
+
+using kmer_t = uint64_t;
+
+class kmer_Set_Light {
+public:
+	size_t number_kmer = 0;
+	size_t number_super_kmer = 0;
+	std::atomic<size_t> number_query{0};
+
+	kmer_Set_Light(unsigned k, unsigned minimizer_length, unsigned log2_mphfs_number, unsigned log2_superbuckets_number,
+	               unsigned cores_number, unsigned bits_to_save, int device = 0)
+	    : _k(k), _m(minimizer_length), _n(log2_mphfs_number), _s(log2_superbuckets_number), _cores(cores_number), _b(bits_to_save), _device(device) {
+		if (blight_check_params(_k, _m, _n, _s, _b) != BLIGHT_OK) throw std::invalid_argument(blight_last_error());
+	}
+	kmer_Set_Light(const kmer_Set_Light&) = delete;
+	kmer_Set_Light& operator=(const kmer_Set_Light&) = delete;
+	~kmer_Set_Light() { blight_index_free(_idx); blight_flat_free(_flat); }
+
+	void construct_index(const std::string& input_file) {
+		blight_index_free(_idx); _idx = nullptr;
+		blight_flat_free(_flat); _flat = nullptr;
+		raise(blight_flat_build_file(input_file.c_str(), _k, _m, _n, _s, _b, _cores, &_flat));
+		adopt();
+	}
+
+	// ours: load an index saved with save_index() (or exported from a reference object)
+	void load_index(const std::string& blob) {
+		blight_index_free(_idx); _idx = nullptr;
+		blight_flat_free(_flat); _flat = nullptr;
+		raise(blight_flat_load(blob.c_str(), &_flat));
+		adopt();
+	}
+	void save_index(const std::string& blob) const { raise(blight_flat_save(_flat, blob.c_str())); }
+
+	// Returns (Good kmer, Erroneous kmers) and adds to number_query; the reference prints them (blight.cpp:792-795).
+	std::pair<uint64_t, uint64_t> file_query(const std::string& query_file) {
+		uint64_t ctr[BLIGHT_N_CTR];
+		raise(blight_query_file_host(need(), query_file.c_str(), ctr));
+		number_query += ctr[BLIGHT_CTR_QUERIES];
+		return {ctr[BLIGHT_CTR_FOUND], ctr[BLIGHT_CTR_NOT_FOUND]};
+	}
+
+	std::vector<int64_t> query_sequence_hash(const std::string& query) {
+		std::vector<int64_t> res(query.size() >= _k ? query.size() - _k + 1 : 0);
+		uint64_t n = 0;
+		raise(blight_query_sequence_host(need(), query.data(), query.size(), res.data(), &n));
+		number_query += n;
+		return res;
+	}
+
+	std::pair<uint32_t, uint32_t> query_sequence_bool(const std::string& query) {
+		uint32_t good = 0, fail = 0;
+		for (int64_t id : query_sequence_hash(query)) (id >= 0 ? good : fail)++;
+		return {good, fail};
+	}
+
+	int64_t query_kmer_hash(kmer_t canon) {
+		int64_t id = -1;
+		raise(blight_query_kmers_host(need(), &canon, 1, &id));
+		number_query += 1;
+		return id;
+	}
+	bool query_kmer_bool(kmer_t canon) { return query_kmer_hash(canon) >= 0; }
+
+	// ours: batched forms of the two calls above
+	std::vector<int64_t> query_kmers_hash(const std::vector<kmer_t>& canon) {
+		std::vector<int64_t> ids(canon.size());
+		raise(blight_query_kmers_host(need(), canon.data(), canon.size(), ids.data()));
+		number_query += canon.size();
+		return ids;
+	}
+
+	const blight_index* device_index() const { return _idx; }
+
+private:
+	static void raise(int rc) {
+		if (rc == BLIGHT_OK) return;
+		const std::string msg = blight_last_error();
+		if (rc == BLIGHT_ERR_INVALID_ARG) throw std::invalid_argument(msg);
+		if (rc == BLIGHT_ERR_INVALID_BASE) throw std::domain_error(msg);
+		throw std::runtime_error(msg);
+	}
+	const blight_index* need() const {
+		if (!_idx) throw std::runtime_error("kmer_Set_Light: construct_index() has not been called");
+		return _idx;
+	}
+	void adopt() {
+		blight_info info;
+		raise(blight_flat_info(_flat, &info));
+		number_kmer = info.number_kmer;
+		number_super_kmer = info.number_super_kmer;
+		raise(blight_index_upload(_flat, _device, &_idx));
+	}
+
+	const unsigned _k, _m, _n, _s, _cores, _b;
+	const int _device;
+	blight_flat* _flat = nullptr;
+	blight_index* _idx = nullptr;
+};

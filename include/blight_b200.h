@@ -40,7 +40,7 @@ typedef struct blight_index blight_index; /* device-resident index */
 #define BLIGHT_CTR_FOUND 0     /* "Good kmer", TP, blight.cpp:784-785,793 */
 #define BLIGHT_CTR_NOT_FOUND 1 /* "Erroneous kmers", FP, blight.cpp:786-787,794 */
 #define BLIGHT_CTR_QUERIES 2   /* number_query, blight.cpp:687-688,795 */
-#define BLIGHT_CTR_INVALID 3   /* bytes that nuc2int would reject (kmer.h:68); non-zero => BLIGHT_ERR_INVALID_BASE */
+#define BLIGHT_CTR_INVALID 3   /* queried k-mers holding a byte nuc2int rejects (kmer.h:68); non-zero => BLIGHT_ERR_INVALID_BASE */
 #define BLIGHT_N_CTR 4
 
 typedef struct blight_info {
@@ -75,6 +75,10 @@ int blight_flat_build_file(const char* unitig_path, uint32_t k, uint32_t m, uint
 /* Same, from sequences already in memory: sequence i = bases[offsets[i] .. offsets[i+1]). */
 int blight_flat_build_seqs(const char* bases, const uint64_t* offsets, uint64_t n_seqs, uint32_t k, uint32_t m,
                            uint32_t n_log2, uint32_t s_log2, uint32_t b, uint32_t threads, blight_flat** out);
+/* Same, sequence i = bases[starts[i] .. starts[i]+lengths[i]) — spans may overlap (unitigs cut from one genome). */
+int blight_flat_build_spans(const char* bases, const uint64_t* starts, const uint64_t* lengths, uint64_t n_seqs,
+                            uint32_t k, uint32_t m, uint32_t n_log2, uint32_t s_log2, uint32_t b, uint32_t threads,
+                            blight_flat** out);
 /* The reference has no index persistence (only mphf::save/load, bbhash.h:731-775); this is ours. */
 int blight_flat_save(const blight_flat* f, const char* path);
 int blight_flat_load(const char* path, blight_flat** out);
@@ -106,7 +110,7 @@ int blight_query_kmers_mini(const blight_index* idx, const uint64_t* d_canon, co
 /* Front end only: canonical k-mers and minimizers of every k-mer of every read, in read order then position
  * (query_sequence_hash's order, blight.cpp:575-591; minimizer_naive, kmer.h:791-810). Read r is
  * d_bases[d_read_off[r] .. d_read_off[r+1]); its k-mers land at d_kmer_off[r].. (d_kmer_off = exclusive prefix of
- * max(0, len-k+1), n_reads+1 entries). d_ctr[BLIGHT_CTR_INVALID] counts rejected bytes. Needs no index: pass k, m. */
+ * max(0, len-k+1), n_reads+1 entries). d_ctr[BLIGHT_CTR_INVALID] counts k-mers holding a rejected byte. Needs no index: pass k, m. */
 int blight_reads_to_kmers(uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
                           const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, uint64_t* d_canon,
                           uint32_t* d_mini, uint64_t* d_ctr, void* stream);

@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure the in-tree libraries exist (cheap no-op when they are up to date)."""
+    import __graft_entry__ as g
+    lib = os.path.join(ROOT, "blight_b200", "lib", "libblight_b200.so")
+    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, "oracle", "libblight_oracle.so")):
+        g.build()
+    yield
