@@ -73,6 +73,7 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 
 	std::vector<DevMphf> mphf(H.n_mphf);
 	uint64_t bits_sectors = 0, pos_sectors = 0;
+	uint32_t small = 1;
 	for (uint64_t g = 0; g < H.n_mphf; g++) {
 		const MphfRec& r = F.mphf[g];
 		DevMphf& d = mphf[g];
@@ -84,8 +85,10 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 		d.fb_count = (uint32_t)r.fb_count;
 		d.nbits = r.nbits ? r.nbits : 1;
 		d.fields_per_sector = 256 / d.nbits;
+		d.fps_magic = (uint32_t)((1ull << 32) / d.fields_per_sector);
 		d.present = r.present;
-		for (int l = 0; l < kLevels; l++) d.dom[l] = r.present ? r.dom[l] : 64;
+		for (int l = 0; l < kLevels; l++) { d.dom[l] = r.present ? r.dom[l] : 64; d.dom32[l] = (uint32_t)d.dom[l]; }
+		if (r.present && r.bits_nwords * 64 >= (1ull << 32)) small = 0;
 		if (r.present) {
 			bits_sectors += (r.bits_nwords * 64 + kChunkBits - 1) / kChunkBits;
 			pos_sectors += (r.nelem + d.fields_per_sector - 1) / d.fields_per_sector;
@@ -168,6 +171,7 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 	v.fb_vals = static_cast<const uint64_t*>(idx->d_fbv);
 	v.k = H.k; v.m = H.m; v.b = H.b; v.lb = F.lb();
 	v.kmask = (1ull << (2 * H.k)) - 1;
+	v.small = small;
 	fill_info(F, &idx->info);
 	idx->info.device_bytes = bytes;
 	*out = idx;

@@ -36,10 +36,11 @@ struct alignas(64) DevMphf {
 	uint32_t fb_count;
 	uint32_t nbits;             // position field width
 	uint32_t fields_per_sector; // floor(256 / nbits)
+	uint32_t fps_magic;         // floor(2^32 / fields_per_sector): rank / fps = umulhi(rank, magic) (+1 fix-up)
 	uint32_t present;
-	uint64_t pad[2];
+	uint32_t pad[3];
 	uint64_t dom[kLevels];      // level domains
-	uint64_t pad2[8];
+	uint32_t dom32[kLevels];    // the same as 32-bit values when the whole group has fewer than 2^32 level bits
 };
 static_assert(sizeof(DevMphf) == 256, "DevMphf is 256 bytes");
 
@@ -53,6 +54,7 @@ struct DevIndexView {
 	const uint64_t* fb_vals;
 	uint64_t kmask;
 	uint32_t k, m, b, lb;
+	uint32_t small;  // every MPHF group has fewer than 2^32 level bits: 32-bit bit arithmetic in the probe
 };
 
 }  // namespace blight

@@ -1,13 +1,16 @@
 // lookup.cuh — the lookup core: one canonical k-mer -> identifier, on the device layout of device_index.hpp.
 //
 // Follows query_get_hash (blight.cpp:716-742) step for step; what changes is how many sectors each step reads.
-//   1. bucket[minimizer]: empty -> -1                                   (blight.cpp:719)        1 x 16 B
-//   2. group = minimizer >> lb, its DevMphf                             (blight.cpp:722)        L1-resident
+//   1. bucket[minimizer]: empty -> -1                                   (blight.cpp:719)        1 x 16 B, L1/L2 resident
+//   2. group = minimizer >> lb, its DevMphf                             (blight.cpp:722)        L1 resident
 //   3. BBHash levels: hash, mulhi, test bit, rank                       (bbhash.h:561-577)      1 sector per level
 //   4. position field, << b, as uint32                                  (blight.cpp:473-482)    1 sector
 //   5. guard pos+k-1 < bucket length (first window only)                (blight.cpp:729)
 //   6. scan 2^b windows of the bucket sequence for canon(window)==x     (blight.cpp:730-739)    1-2 sectors (b<=6)
 //   7. id = rank + id_offset, else -1                                   (blight.cpp:736,741)
+//
+// L2 residency is steered per array: level bits (small, probed ~2x per k-mer) are loaded evict_last, position
+// sectors (large, touched once) evict_first and not allocated in L1, sequences with the default policy.
 #pragma once
 #include <cstdint>
 
@@ -16,10 +19,31 @@
 
 namespace blight {
 
-__device__ __forceinline__ void ld_sector(const uint32_t* p, uint32_t (&w)[8]) {
-	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+// one level-bits sector: 7 words of bits + ones-before-this-chunk; kept in L2 as long as possible
+__device__ __forceinline__ void ld_bits_sector(const uint32_t* p, uint32_t (&w)[8]) {
+	asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 	             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
 	             : "l"(p));
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+
+__device__ __forceinline__ uint32_t ld_u32_stream(const uint32_t* p, uint64_t pol) {
+	uint32_t v;
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+	return v;
+}
+
+// word j (0..6) of a sector held in registers, without dynamic register indexing
+__device__ __forceinline__ uint32_t pick7(const uint32_t (&w)[8], uint32_t j) {
+	const bool b0 = j & 1, b1 = j & 2, b2 = j & 4;
+	const uint32_t s01 = b0 ? w[1] : w[0], s23 = b0 ? w[3] : w[2], s45 = b0 ? w[5] : w[4];
+	const uint32_t lo = b1 ? s23 : s01, hi = b1 ? w[6] : s45;
+	return b2 ? hi : lo;
 }
 
 // Scans `nwin` consecutive k-mer windows of the packed sequence starting at nucleotide P for x or its reverse
@@ -55,41 +79,66 @@ __device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, u
 	return false;
 }
 
-__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini) {
+template <bool SMALL>
+__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini, uint64_t pol_stream) {
 	const uint4 bd = __ldg(I.bucket + mini);
 	if (bd.z == 0) return -1;
 	const DevMphf* __restrict__ M = I.mphf + (mini >> I.lb);
-	const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(M));      // bits_sector_base, pos_sector_base
+	const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(M));  // bits_sector_base, pos_sector_base
 	const uint32_t* bits = I.bits + ((((uint64_t)m0.y << 32) | m0.x) << 3);
 
 	// BBHash levels (bbhash.h:619-639): first level whose bit is set wins
-	uint64_t s0 = 0, s1 = 0, off = 0, rank = ~0ull;
-	#pragma unroll 1
-	for (int level = 0; level < kLevels; level++) {
-		uint64_t h;
-		if (level == 0) h = s0 = hash_bis(x, kSeed0);
-		else if (level == 1) h = s1 = hash_bis(x, kSeed1);
-		else h = xs128_next(s0, s1);
-		const uint64_t dom = __ldg(&M->dom[level]);
-		const uint64_t bit = off + __umul64hi(h, dom);
-		const uint64_t chunk = bit / kChunkBits;
-		const uint32_t r = (uint32_t)(bit - chunk * kChunkBits);
-		uint32_t w[8];
-		ld_sector(bits + (chunk << 3), w);
+	uint64_t s0 = 0, s1 = 0;
+	uint32_t w[8];
+	uint32_t r = 0;
+	bool hit = false;
+	if (SMALL) {
+		uint32_t off = 0;
+		#pragma unroll 1
+		for (int level = 0; level < kLevels; level++) {
+			uint64_t h;
+			if (level == 0) h = s0 = hash_bis(x, kSeed0);
+			else if (level == 1) h = s1 = hash_bis(x, kSeed1);
+			else h = xs128_next(s0, s1);
+			const uint32_t dom = __ldg(&M->dom32[level]);
+			// fastmod64 (bbhash.h:660-662) with a 32-bit domain: hi64(h * dom)
+			const uint32_t bit = off + (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * dom + __umulhi((uint32_t)h, dom)) >> 32);
+			const uint32_t chunk = bit / kChunkBits;
+			r = bit - chunk * kChunkBits;
+			ld_bits_sector(bits + ((uint64_t)chunk << 3), w);
+			if ((pick7(w, r >> 5) >> (r & 31)) & 1u) { hit = true; break; }
+			off += dom;
+		}
+	} else {
+		uint64_t off = 0;
+		#pragma unroll 1
+		for (int level = 0; level < kLevels; level++) {
+			uint64_t h;
+			if (level == 0) h = s0 = hash_bis(x, kSeed0);
+			else if (level == 1) h = s1 = hash_bis(x, kSeed1);
+			else h = xs128_next(s0, s1);
+			const uint64_t dom = __ldg(&M->dom[level]);
+			const uint64_t bit = off + __umul64hi(h, dom);
+			const uint64_t chunk = bit / kChunkBits;
+			r = (uint32_t)(bit - chunk * kChunkBits);
+			ld_bits_sector(bits + (chunk << 3), w);
+			if ((pick7(w, r >> 5) >> (r & 31)) & 1u) { hit = true; break; }
+			off += dom;
+		}
+	}
+	const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(M) + 1);  // id_offset, fb_off
+	const uint4 m2 = __ldg(reinterpret_cast<const uint4*>(M) + 2);  // fb_count, nbits, fields_per_sector, fps_magic
+	uint32_t rank;
+	if (hit) {
+		// bitVector::rank (bbhash.h:467-480): ones before this chunk + ones below the bit inside the chunk
 		const uint32_t j = r >> 5, bi = r & 31;
-		uint32_t hit = 0, cnt = w[7];
+		rank = w[7];
 		#pragma unroll
 		for (int i = 0; i < 7; i++) {
 			const uint32_t below = (i < (int)j) ? 0xFFFFFFFFu : ((i == (int)j) ? ((1u << bi) - 1u) : 0u);
-			cnt += __popc(w[i] & below);
-			hit |= (i == (int)j) ? ((w[i] >> bi) & 1u) : 0u;
+			rank += __popc(w[i] & below);
 		}
-		if (hit) { rank = cnt; break; }
-		off += dom;
-	}
-	const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(M) + 1);  // id_offset, fb_off
-	const uint4 m2 = __ldg(reinterpret_cast<const uint4*>(M) + 2);  // fb_count, nbits, fields_per_sector, present
-	if (rank == ~0ull) {
+	} else {
 		// fallback map (bbhash.h:567-575), sorted by key
 		const uint64_t fb_off = ((uint64_t)m1.w << 32) | m1.z;
 		uint32_t lo = 0, hi = m2.x;
@@ -98,22 +147,23 @@ __device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x,
 			if (__ldg(I.fb_keys + fb_off + mid) < x) lo = mid + 1; else hi = mid;
 		}
 		if (lo >= m2.x || __ldg(I.fb_keys + fb_off + lo) != x) return -1;
-		rank = __ldg(I.fb_vals + fb_off + lo);
+		rank = (uint32_t)__ldg(I.fb_vals + fb_off + lo);
 	}
 	// position field (blight.cpp:473-482): uint32 arithmetic, << b
 	const uint32_t nbits = m2.y, fps = m2.z;
-	const uint64_t psec = rank / fps;
-	const uint32_t slot = (uint32_t)(rank - psec * fps);
+	uint32_t psec = __umulhi(rank, m2.w);  // floor(rank / fps) or one less
+	uint32_t slot = rank - psec * fps;
+	if (slot >= fps) { slot -= fps; psec++; }
 	const uint32_t* ps = I.pos + (((((uint64_t)m0.w << 32) | m0.z) + psec) << 3);
 	const uint32_t o = slot * nbits, ow = o >> 5;
-	const uint32_t p0 = __ldg(ps + ow), p1 = __ldg(ps + (ow < 7 ? ow + 1 : 7));
+	const uint32_t p0 = ld_u32_stream(ps + ow, pol_stream), p1 = ld_u32_stream(ps + (ow < 7 ? ow + 1 : 7), pol_stream);
 	uint32_t field = __funnelshift_r(p0, p1, o & 31);
 	if (nbits < 32) field &= (1u << nbits) - 1u;
 	const uint32_t pos = field << I.b;
 	if (!((uint64_t)pos + I.k - 1 < (uint64_t)bd.z)) return -1;
 	const uint64_t P = (((uint64_t)bd.y << 32) | bd.x) + pos;
 	if (!scan_windows(I.seq, P, I.k, 1u << I.b, x, rc64(x, I.k))) return -1;
-	return (int64_t)(rank + (((uint64_t)m1.y << 32) | m1.x));
+	return (int64_t)((uint64_t)rank + (((uint64_t)m1.y << 32) | m1.x));
 }
 
 }  // namespace blight
