@@ -46,34 +46,89 @@ __device__ __forceinline__ uint32_t pick7(const uint32_t (&w)[8], uint32_t j) {
 	return b2 ? hi : lo;
 }
 
-// Scans `nwin` consecutive k-mer windows of the packed sequence starting at nucleotide P for x or its reverse
-// complement rx. canon(window) == x  <=>  window == x or window == rx, because x is canonical (x <= rx).
-__device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
-                                             uint64_t x, uint64_t rx) {
+// Reference loop form of the 2^b-window scan (blight.cpp:730-739): slide one base at a time. Used for k < 8 or b < 3.
+// canon(window) == x  <=>  window == x or window == rx, because x is canonical (x <= rx).
+__device__ __noinline__ bool scan_windows_loop(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
+                                               uint64_t x, uint64_t rx) {
 	const uint64_t wi = P >> 4;
 	const uint32_t s = 2u * (uint32_t)(P & 15);
 	const uint32_t* q = seq + wi;
 	uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-	// top = the 32 nucleotides starting at P; feed = the nucleotides after them
-	uint32_t top_hi = __funnelshift_l(b, a, s), top_lo = __funnelshift_l(c, b, s);
-	const uint32_t sh = 64 - 2 * k;  // window = top >> sh
-	const uint32_t xl = (uint32_t)x, rl = (uint32_t)rx;
+	uint32_t top_hi = __funnelshift_l(b, a, s), top_lo = __funnelshift_l(c, b, s);  // the 32 bases starting at P
+	const uint32_t sh = 64 - 2 * k;                                                  // window = top >> sh
 	q += 3;
-	uint32_t prev = c;
-	for (uint32_t j = 0; j < nwin; j += 16) {
-		const uint32_t nxt = __ldg(q++);
-		uint32_t feed = __funnelshift_l(nxt, prev, s);
-		prev = nxt;
+	uint32_t prev = c, feed = 0;
+	for (uint32_t j = 0; j < nwin; j++) {
+		if ((j & 15) == 0) {
+			const uint32_t nxt = __ldg(q++);
+			feed = __funnelshift_l(nxt, prev, s);
+			prev = nxt;
+		}
+		const uint64_t w = (((uint64_t)top_hi << 32) | top_lo) >> sh;
+		if (w == x || w == rx) return true;
+		top_hi = __funnelshift_l(top_lo, top_hi, 2);
+		top_lo = __funnelshift_l(feed, top_lo, 2);
+		feed <<= 2;
+	}
+	return false;
+}
+
+// window j of the sequence starting at base P equals x or rx? (three L1-resident word loads)
+__device__ __forceinline__ bool window_matches(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint64_t x, uint64_t rx) {
+	const uint32_t* q = seq + (P >> 4);
+	const uint32_t s = 2u * (uint32_t)(P & 15);
+	const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+	const uint64_t w = ((((uint64_t)__funnelshift_l(b, a, s)) << 32) | __funnelshift_l(c, b, s)) >> (64 - 2 * k);
+	return w == x || w == rx;
+}
+
+// The same scan, branch-free and two windows per instruction: the first 8 bases (16 bits) of every window are
+// compared against the first 8 bases of x and of rx with half-word SIMD compares; windows are handled in 8 residue
+// classes (start offset mod 8), so that in the text shifted by the class offset every candidate prefix is half-word
+// aligned. Survivors (the true match, plus ~2^-16 false candidates per window) are verified in full.
+// Requires k >= 8 and nwin >= 8 (a power of two).
+__device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
+                                             uint64_t x, uint64_t rx) {
+	const uint32_t* q = seq + (P >> 4);
+	const uint32_t s = 2u * (uint32_t)(P & 15);
+	const uint32_t X2 = (uint32_t)(x >> (2 * k - 16)) * 0x00010001u;
+	const uint32_t R2 = (uint32_t)(rx >> (2 * k - 16)) * 0x00010001u;
+	uint32_t wprev = __ldg(q);
+	for (uint32_t base = 0; base < nwin; base += 64, q += 4) {
+		// A[i] = bases [P + base + 16 i, +16): the text of this 64-window chunk, re-aligned to word boundaries
+		const uint32_t nwords = nwin - base >= 64 ? 4 : (nwin - base + 15) / 16;  // words of window starts
+		uint32_t A[5];
 		#pragma unroll
-		for (int t = 0; t < 16; t++) {
-			const uint32_t wl = sh >= 32 ? (top_hi >> (sh - 32)) : __funnelshift_r(top_lo, top_hi, sh);
-			if (wl == xl || wl == rl) {
-				const uint64_t w = (((uint64_t)top_hi << 32) | top_lo) >> sh;
-				if ((w == x || w == rx) && j + t < nwin) return true;
+		for (int i = 0; i < 5; i++) {
+			const uint32_t wn = (i <= (int)nwords) ? __ldg(q + i + 1) : 0u;
+			A[i] = __funnelshift_l(wn, wprev, s);
+			wprev = wn;
+		}
+		wprev = __ldg(q + 4);
+		uint32_t acc0 = 0, acc1 = 0;  // candidate windows: bit (16*(1-h) + r + 8*(i&1)) of acc[i>>1]  <->  window r + 8*(2i+h)
+		#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			if (i < (int)nwords) {
+				#pragma unroll
+				for (int r = 0; r < 8; r++) {
+					const uint32_t S = r ? __funnelshift_l(A[i + 1], A[i], 2 * r) : A[i];
+					const uint32_t c = __vcmpeq2(S, X2) | __vcmpeq2(S, R2);
+					const uint32_t K = 0x00010001u << (r + 8 * (i & 1));
+					if (i < 2) acc0 |= c & K; else acc1 |= c & K;
+				}
 			}
-			top_hi = __funnelshift_l(top_lo, top_hi, 2);
-			top_lo = __funnelshift_l(feed, top_lo, 2);
-			feed <<= 2;
+		}
+		if (nwin - base == 8) acc0 &= 0xFFFF0000u;  // only the upper half-word of word 0 holds window starts
+		#pragma unroll 1
+		for (int half = 0; half < 2; half++) {
+			uint32_t acc = half ? acc1 : acc0;
+			while (acc) {
+				const uint32_t bit = 31 - __clz(acc);  // earliest window first is not required: any match gives the same answer
+				acc &= ~(1u << bit);
+				const uint32_t h = bit >= 16 ? 0u : 1u, bb = bit & 15u;
+				const uint32_t j = (bb & 7u) + 8u * (2u * (2u * half + (bb >> 3)) + h);
+				if (window_matches(seq, P + base + j, k, x, rx)) return true;
+			}
 		}
 	}
 	return false;
@@ -162,7 +217,9 @@ __device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x,
 	const uint32_t pos = field << I.b;
 	if (!((uint64_t)pos + I.k - 1 < (uint64_t)bd.z)) return -1;
 	const uint64_t P = (((uint64_t)bd.y << 32) | bd.x) + pos;
-	if (!scan_windows(I.seq, P, I.k, 1u << I.b, x, rc64(x, I.k))) return -1;
+	const uint64_t rx = rc64(x, I.k);
+	const bool ok = (I.k >= 8 && I.b >= 3) ? scan_windows(I.seq, P, I.k, 1u << I.b, x, rx) : scan_windows_loop(I.seq, P, I.k, 1u << I.b, x, rx);
+	if (!ok) return -1;
 	return (int64_t)((uint64_t)rank + (((uint64_t)m1.y << 32) | m1.x));
 }
 
