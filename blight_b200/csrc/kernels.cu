@@ -38,19 +38,42 @@ template <bool HAS_MINI, bool SMALL>
 __global__ void __launch_bounds__(kThreads) k_lookup_kmers(DevIndexView I, const uint64_t* __restrict__ canon,
                                                            const uint32_t* __restrict__ mini, uint64_t n,
                                                            int64_t* __restrict__ ids) {
-	const uint64_t pol = l2_policy_evict_first();
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 		const uint64_t x = __ldcs(canon + i);
 		const uint32_t mn = HAS_MINI ? __ldcs(mini + i) : minimizer_of_kmer(x, I.k, I.m);
-		__stcs(reinterpret_cast<long long*>(ids + i), (long long)lookup_one<SMALL>(I, x, mn, pol));
+		__stcs(reinterpret_cast<long long*>(ids + i), (long long)lookup_one<SMALL>(I, x, mn));
 	}
 }
 
 enum ReadsMode { kEmitPairs = 0, kLookupIds = 1, kLookupCount = 2 };
 
-// first read r in [lo, hi] with off[r+1] > p, i.e. the read containing base position p (or the gap before it)
-__device__ __forceinline__ uint64_t find_read(const uint64_t* __restrict__ off, uint64_t lo, uint64_t hi, uint64_t p) {
+// first read r in [0, n_reads) with off[r+1] > p, i.e. the read containing base position p (or the gap before it).
+// Starts from the position a uniform read length would give and brackets the answer exponentially: 2-3 loads for
+// the usual near-uniform batches, a plain binary search in the worst case.
+__device__ __forceinline__ uint64_t find_read(const uint64_t* __restrict__ off, uint64_t n_reads, double reads_per_base, uint64_t p) {
+	uint64_t g = (uint64_t)((double)p * reads_per_base);
+	if (g > n_reads - 1) g = n_reads - 1;
+	uint64_t lo, hi;  // invariant: answer in [lo, hi]
+	if (__ldg(off + g + 1) > p) {
+		hi = g; lo = g;
+		uint64_t step = 1;
+		while (lo > 0) {
+			const uint64_t c = lo > step ? lo - step : 0;
+			if (__ldg(off + c + 1) > p) { hi = c; lo = c; step <<= 1; }
+			else { lo = c + 1; break; }
+		}
+	} else {
+		lo = g + 1; hi = lo;
+		uint64_t step = 1;
+		while (hi < n_reads - 1 && !(__ldg(off + hi + 1) > p)) {
+			lo = hi + 1;
+			hi = hi + step < n_reads ? hi + step : n_reads - 1;
+			step <<= 1;
+		}
+		if (hi > n_reads - 1) hi = n_reads - 1;
+		if (lo > hi) lo = hi;
+	}
 	while (lo < hi) {
 		const uint64_t mid = (lo + hi) >> 1;
 		if (__ldg(off + mid + 1) > p) hi = mid; else lo = mid + 1;
@@ -77,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 	const uint32_t mmask = (1u << (2 * m)) - 1u;
 	const uint64_t n_strips = (total_bases + kStrip - 1) / kStrip;
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
-	const uint64_t pol = l2_policy_evict_first();
+	const double reads_per_base = (double)n_reads / (double)total_bases;
 	uint32_t found = 0, notfound = 0, invalid = 0;
 
 	for (uint64_t strip = (uint64_t)blockIdx.x * kWarps + wid; strip < n_strips; strip += warp_stride) {
@@ -110,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 		}
 		// read containing the first position of the strip (lane 0 searches, everybody starts from there)
 		uint64_t r = 0;
-		if (lane == 0) r = find_read(read_off, 0, n_reads - 1, t0);
+		if (lane == 0) r = find_read(read_off, n_reads, reads_per_base, t0);
 		r = __shfl_sync(0xffffffffu, r, 0);
 		__syncwarp();
 
@@ -150,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 				__stcs(reinterpret_cast<unsigned long long*>(out_canon + o), (unsigned long long)x);
 				__stcs(out_mini + o, mn);
 			} else {
-				const int64_t id = lookup_one<SMALL>(I, x, mn, pol);
+				const int64_t id = lookup_one<SMALL>(I, x, mn);
 				if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + __ldg(kmer_off + r) + (p - rbeg)), (long long)id);
 				if (id >= 0) found++; else notfound++;
 			}

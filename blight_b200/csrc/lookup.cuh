@@ -12,6 +12,8 @@
 // L2 residency is steered per array: level bits (small, probed ~2x per k-mer) are loaded evict_last, position
 // sectors (large, touched once) evict_first and not allocated in L1, sequences with the default policy.
 #pragma once
+#include <cuda_fp16.h>
+
 #include <cstdint>
 
 #include "device_index.hpp"
@@ -26,16 +28,19 @@ __device__ __forceinline__ void ld_bits_sector(const uint32_t* p, uint32_t (&w)[
 	             : "l"(p));
 }
 
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-	uint64_t pol;
-	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-	return pol;
+// one position sector: touched once per query, so neither L1 nor L2 should keep it
+__device__ __forceinline__ void ld_pos_sector(const uint32_t* p, uint32_t (&w)[8]) {
+	asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+	             : "l"(p));
 }
 
-__device__ __forceinline__ uint32_t ld_u32_stream(const uint32_t* p, uint64_t pol) {
-	uint32_t v;
-	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-	return v;
+// word j (0..7) of a sector held in registers
+__device__ __forceinline__ uint32_t pick8(const uint32_t (&w)[8], uint32_t j) {
+	const bool b0 = j & 1, b1 = j & 2, b2 = j & 4;
+	const uint32_t s01 = b0 ? w[1] : w[0], s23 = b0 ? w[3] : w[2], s45 = b0 ? w[5] : w[4], s67 = b0 ? w[7] : w[6];
+	const uint32_t lo = b1 ? s23 : s01, hi = b1 ? s67 : s45;
+	return b2 ? hi : lo;
 }
 
 // word j (0..6) of a sector held in registers, without dynamic register indexing
@@ -83,7 +88,7 @@ __device__ __forceinline__ bool window_matches(const uint32_t* __restrict__ seq,
 }
 
 // The same scan, branch-free and two windows per instruction: the first 8 bases (16 bits) of every window are
-// compared against the first 8 bases of x and of rx with half-word SIMD compares; windows are handled in 8 residue
+// compared against the first 8 bases of x and of rx with half-word SIMD compares (HSET2); windows are handled in 8 residue
 // classes (start offset mod 8), so that in the text shifted by the class offset every candidate prefix is half-word
 // aligned. Survivors (the true match, plus ~2^-16 false candidates per window) are verified in full.
 // Requires k >= 8 and nwin >= 8 (a power of two).
@@ -91,8 +96,14 @@ __device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, u
                                              uint64_t x, uint64_t rx) {
 	const uint32_t* q = seq + (P >> 4);
 	const uint32_t s = 2u * (uint32_t)(P & 15);
-	const uint32_t X2 = (uint32_t)(x >> (2 * k - 16)) * 0x00010001u;
-	const uint32_t R2 = (uint32_t)(rx >> (2 * k - 16)) * 0x00010001u;
+	// Half-word equality through the fp16x2 compare unit (one HSET2 per two windows and target). Bit 14 (the top
+	// exponent bit) is cleared on both sides so no half is ever NaN/Inf: equal bits => equal floats, hence no false
+	// negatives; +0/-0 and the dropped bit only add false candidates, which the full verification rejects.
+	const uint32_t kNoNan = 0xBFFFBFFFu;
+	const uint32_t X2u = ((uint32_t)(x >> (2 * k - 16)) * 0x00010001u) & kNoNan;
+	const uint32_t R2u = ((uint32_t)(rx >> (2 * k - 16)) * 0x00010001u) & kNoNan;
+	const __half2 X2 = *reinterpret_cast<const __half2*>(&X2u);
+	const __half2 R2 = *reinterpret_cast<const __half2*>(&R2u);
 	uint32_t wprev = __ldg(q);
 	for (uint32_t base = 0; base < nwin; base += 64, q += 4) {
 		// A[i] = bases [P + base + 16 i, +16): the text of this 64-window chunk, re-aligned to word boundaries
@@ -111,8 +122,9 @@ __device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, u
 			if (i < (int)nwords) {
 				#pragma unroll
 				for (int r = 0; r < 8; r++) {
-					const uint32_t S = r ? __funnelshift_l(A[i + 1], A[i], 2 * r) : A[i];
-					const uint32_t c = __vcmpeq2(S, X2) | __vcmpeq2(S, R2);
+					const uint32_t Su = (r ? __funnelshift_l(A[i + 1], A[i], 2 * r) : A[i]) & kNoNan;
+					const __half2 S = *reinterpret_cast<const __half2*>(&Su);
+					const uint32_t c = __heq2_mask(S, X2) | __heq2_mask(S, R2);
 					const uint32_t K = 0x00010001u << (r + 8 * (i & 1));
 					if (i < 2) acc0 |= c & K; else acc1 |= c & K;
 				}
@@ -135,7 +147,7 @@ __device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, u
 }
 
 template <bool SMALL>
-__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini, uint64_t pol_stream) {
+__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini) {
 	const uint4 bd = __ldg(I.bucket + mini);
 	if (bd.z == 0) return -1;
 	const DevMphf* __restrict__ M = I.mphf + (mini >> I.lb);
@@ -211,8 +223,9 @@ __device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x,
 	if (slot >= fps) { slot -= fps; psec++; }
 	const uint32_t* ps = I.pos + (((((uint64_t)m0.w << 32) | m0.z) + psec) << 3);
 	const uint32_t o = slot * nbits, ow = o >> 5;
-	const uint32_t p0 = ld_u32_stream(ps + ow, pol_stream), p1 = ld_u32_stream(ps + (ow < 7 ? ow + 1 : 7), pol_stream);
-	uint32_t field = __funnelshift_r(p0, p1, o & 31);
+	uint32_t pw[8];
+	ld_pos_sector(ps, pw);
+	uint32_t field = __funnelshift_r(pick8(pw, ow), pick8(pw, (ow + 1) & 7), o & 31);
 	if (nbits < 32) field &= (1u << nbits) - 1u;
 	const uint32_t pos = field << I.b;
 	if (!((uint64_t)pos + I.k - 1 < (uint64_t)bd.z)) return -1;
