@@ -26,7 +26,7 @@ SYMBOLS = [
     "blight_flat_slice", "blight_flat_group_sizes", "blight_index_upload", "blight_index_free", "blight_index_info",
     "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
-    "blight_query_kmers_host", "blight_launch_count",
+    "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
 ]
 
 
@@ -89,6 +89,9 @@ def lib() -> C.CDLL:
     L.blight_query_sequence_host.argtypes = [vp, vp, u64, vp, C.POINTER(u64)]
     L.blight_query_reads_host.argtypes = [vp, vp, vp, u64, vp, vp]
     L.blight_query_kmers_host.argtypes = [vp, vp, u64, vp]
+    L.blight_owner_count.argtypes = [vp, u64, vp, u32, u32, vp, vp]
+    L.blight_owner_scatter.argtypes = [vp, vp, u64, vp, u32, u32, vp, vp, vp, vp, vp]
+    L.blight_scatter_ids.argtypes = [vp, vp, u64, vp, vp]
     L.blight_launch_count.restype = u64
     _lib = L
     return L

@@ -1,0 +1,207 @@
+"""Multi-GPU layer of the query path: one process per GPU, torch.distributed for the plumbing.
+
+ReplicaSet       small / medium indices: the whole index on every GPU, reads split in contiguous chunks, no collective
+                 on the data path (the three counters are summed once at the end).
+PartitionedSet   large indices: the 2^n MPHF groups are cut into `world` contiguous ranges balanced by k-mer count; a
+                 rank holds only its slice (blight_flat_slice). Per batch: front end on the rank that holds the reads
+                 -> bin (canon, minimizer) by owner -> ONE all-to-all out -> lookup at the owner -> ONE all-to-all back
+                 -> scatter into read order. Ids are global in both modes.
+
+The routing (`PartitionPlan`, `exchange_lookup`) is device-agnostic torch code so that world_size-2 `gloo` tests on CPU
+exercise exactly the logic the NCCL path runs; on CUDA the binning and the final scatter are the library's own kernels
+(blight_owner_count / blight_owner_scatter / blight_scatter_ids), never a torch sort.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import api
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous chunk [lo, hi) of n items for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class PartitionPlan:
+    """Contiguous ranges of MPHF groups per rank. cuts has world+1 ascending entries, cuts[0]=0, cuts[-1]=n_mphf."""
+    cuts: List[int]
+    lb: int  # log2(buckets per MPHF group): group = minimizer >> lb (blight.cpp:722)
+
+    @property
+    def world(self) -> int:
+        return len(self.cuts) - 1
+
+    @staticmethod
+    def balanced(group_sizes: np.ndarray, world: int, lb: int) -> "PartitionPlan":
+        """Cuts after the group at which the running k-mer count first reaches r/world of the total (every rank gets
+        at least one group when there are enough groups)."""
+        g = np.asarray(group_sizes, dtype=np.float64)
+        n = len(g)
+        if world > n:
+            raise ValueError(f"cannot partition {n} MPHF groups over {world} ranks (use n >= log2(world))")
+        csum = np.cumsum(g)
+        total = csum[-1] if n else 0.0
+        cuts = [0]
+        for r in range(1, world):
+            c = int(np.searchsorted(csum, total * r / world, side="left")) + 1
+            c = max(c, cuts[-1] + 1)          # at least one group per rank
+            c = min(c, n - (world - r))       # leave one group for each remaining rank
+            cuts.append(c)
+        cuts.append(n)
+        return PartitionPlan(cuts, lb)
+
+    def owner_of(self, mini: torch.Tensor) -> torch.Tensor:
+        """Owner rank of each minimizer (any device)."""
+        g = (mini.to(torch.int64) & 0xFFFFFFFF) >> self.lb
+        inner = torch.tensor(self.cuts[1:-1], dtype=torch.int64, device=mini.device)
+        return torch.searchsorted(inner, g, right=True)
+
+    def group_range(self, rank: int) -> Tuple[int, int]:
+        return self.cuts[rank], self.cuts[rank + 1]
+
+
+def _torch_bin(canon: torch.Tensor, mini: torch.Tensor, plan: PartitionPlan):
+    """Device-agnostic binning (used on CPU by the gloo tests): stable sort by owner."""
+    owner = plan.owner_of(mini)
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=plan.world).to(torch.int64)
+    return canon[order], mini[order], order, counts
+
+
+def _cuda_bin(canon: torch.Tensor, mini: torch.Tensor, plan: PartitionPlan):
+    """Binning with the library's kernels: count, prefix on the device, warp-aggregated scatter."""
+    L = api.lib()
+    n = canon.numel()
+    dev = canon.device
+    st = torch.cuda.current_stream().cuda_stream
+    cuts = torch.tensor(plan.cuts, dtype=torch.int32, device=dev)
+    counts = torch.zeros(plan.world, dtype=torch.int64, device=dev)
+    api._check(L.blight_owner_count(mini.data_ptr(), n, cuts.data_ptr(), plan.world, plan.lb, counts.data_ptr(), st))
+    cursors = torch.cumsum(counts, 0) - counts
+    send_canon = torch.empty_like(canon)
+    send_mini = torch.empty_like(mini)
+    send_src = torch.empty(n, dtype=torch.int64, device=dev)
+    api._check(L.blight_owner_scatter(canon.data_ptr(), mini.data_ptr(), n, cuts.data_ptr(), plan.world, plan.lb,
+                                      cursors.data_ptr(), send_canon.data_ptr(), send_mini.data_ptr(), send_src.data_ptr(), st))
+    return send_canon, send_mini, send_src, counts
+
+
+def _cuda_scatter(ids_back: torch.Tensor, src: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.int64, device=ids_back.device)
+    api._check(api.lib().blight_scatter_ids(ids_back.data_ptr(), src.data_ptr(), n, out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def exchange_lookup(canon: torch.Tensor, mini: torch.Tensor, plan: PartitionPlan,
+                    lookup_local: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], group=None) -> torch.Tensor:
+    """ids for (canon, mini) pairs when every rank holds only its group range.
+    lookup_local(canon, mini) -> int64 ids answers pairs whose groups this rank owns."""
+    world = dist.get_world_size(group)
+    assert world == plan.world
+    n = canon.numel()
+    on_cuda = canon.is_cuda
+    send_canon, send_mini, src, counts = (_cuda_bin if on_cuda else _torch_bin)(canon.contiguous(), mini.contiguous(), plan)
+    # split sizes: one small all-to-all of the counts, then the payloads
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts, group=group)
+    in_splits = counts.tolist()
+    out_splits = recv_counts.tolist()
+    m = int(sum(out_splits))
+    recv_canon = torch.empty(m, dtype=canon.dtype, device=canon.device)
+    recv_mini = torch.empty(m, dtype=mini.dtype, device=mini.device)
+    dist.all_to_all_single(recv_canon, send_canon, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+    dist.all_to_all_single(recv_mini, send_mini, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+    ids_remote = lookup_local(recv_canon, recv_mini)
+    ids_back = torch.empty(n, dtype=torch.int64, device=canon.device)
+    dist.all_to_all_single(ids_back, ids_remote.contiguous(), output_split_sizes=in_splits, input_split_sizes=out_splits, group=group)
+    if on_cuda:
+        return _cuda_scatter(ids_back, src, n)
+    out = torch.empty(n, dtype=torch.int64, device=canon.device)
+    out[src] = ids_back
+    return out
+
+
+def all_reduce_counters(ctr: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of [found, not_found, queries, invalid] over ranks (the only collective of replica mode)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(ctr, op=dist.ReduceOp.SUM, group=group)
+    return ctr
+
+
+class ReplicaSet:
+    """Whole index on every GPU; each rank queries its contiguous chunk of the reads."""
+
+    def __init__(self, flat: api.FlatIndex, device: int, group=None):
+        self.group = group
+        self.index = flat.upload(device)
+        self.k = self.index.k
+
+    def query_reads_sharded(self, bases: torch.Tensor, read_off: torch.Tensor, want_ids: bool = True):
+        """bases / read_off describe the WHOLE batch (same on every rank, on this rank's device); returns this rank's
+        (ids of its chunk or None, global counters)."""
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        n_reads = read_off.numel() - 1
+        lo, hi = shard_range(n_reads, rank, world)
+        off = read_off[lo:hi + 1].contiguous()
+        b0, b1 = int(off[0]), int(off[-1])
+        sub = bases[b0:b1]
+        if (sub.data_ptr() & 15) != 0:
+            sub = sub.clone()  # keep the 16-byte aligned fast path of the front end
+        off = off - b0
+        lens = off[1:] - off[:-1]
+        nk = torch.clamp(lens - (self.k - 1), min=0)
+        koff = torch.zeros(hi - lo + 1, dtype=torch.int64, device=bases.device)
+        torch.cumsum(nk, 0, out=koff[1:])
+        total = int(koff[-1])
+        ids, ctr = self.index.query_reads(sub, off, koff, total, want_ids=want_ids)
+        return (ids[:total] if want_ids else None), all_reduce_counters(ctr, self.group)
+
+
+class PartitionedSet:
+    """Minimizer-bucket partition: this rank holds MPHF groups [cuts[rank], cuts[rank+1])."""
+
+    def __init__(self, plan: PartitionPlan, local_flat: api.FlatIndex, device: int, k: int, m: int, group=None):
+        self.plan, self.group, self.k, self.m = plan, group, k, m
+        self.index = local_flat.upload(device)
+
+    @classmethod
+    def from_full(cls, flat: Optional[api.FlatIndex], device: int, workdir: str, group=None) -> "PartitionedSet":
+        """Rank 0 holds the full flat index: it plans, slices and saves one blob per rank; every rank loads its own."""
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        meta = [None]
+        if rank == 0:
+            info = flat.info()
+            lb = 2 * info["m"] - 1 - info["n_log2"]
+            plan = PartitionPlan.balanced(flat.group_sizes(), world, lb)
+            for r in range(world):
+                a, b = plan.group_range(r)
+                flat.slice(a, b).save(os.path.join(workdir, f"part{r}.blflat"))
+            meta = [(plan.cuts, lb, info["k"], info["m"])]
+        dist.broadcast_object_list(meta, src=0, group=group)
+        cuts, lb, k, m = meta[0]
+        local = api.FlatIndex.load(os.path.join(workdir, f"part{rank}.blflat"))
+        return cls(PartitionPlan(list(cuts), lb), local, device, k, m, group)
+
+    def query_kmers(self, canon: torch.Tensor, mini: torch.Tensor) -> torch.Tensor:
+        return exchange_lookup(canon, mini, self.plan, lambda c, mn: self.index.query_kmers(c, mini=mn), self.group)
+
+    def query_reads(self, bases: torch.Tensor, read_off: torch.Tensor, kmer_off: torch.Tensor, total_kmers: int):
+        """Reads held by THIS rank -> (ids in read order, local counters [found, not_found, queries, invalid])."""
+        canon, mini, fctr = api.reads_to_kmers(self.k, self.m, bases, read_off, kmer_off, total_kmers)
+        ids = self.query_kmers(canon.contiguous(), mini.contiguous())
+        found = (ids >= 0).sum()
+        ctr = torch.stack([found, ids.numel() - found, torch.tensor(ids.numel(), device=ids.device), fctr[api.CTR_INVALID]]).to(torch.int64)
+        return ids, ctr

@@ -138,6 +138,19 @@ int blight_query_reads_host(const blight_index* idx, const char* bases, const ui
 /* query_kmer_hash over a host array of canonical k-mers. */
 int blight_query_kmers_host(const blight_index* idx, const uint64_t* canon, uint64_t n, int64_t* ids_out);
 
+/* ---- bucket-partitioned multi-GPU mode: the kernels either side of the all-to-all (no reference counterpart; the
+ * owner rule is the reference's MPHF selection minimizer / number_bucket_per_mphf, blight.cpp:722) ---------------- */
+
+/* d_counts[o] += number of k-mers whose MPHF group (minimizer >> lb) lies in [d_group_cuts[o], d_group_cuts[o+1]). */
+int blight_owner_count(const uint32_t* d_mini, uint64_t n, const uint32_t* d_group_cuts, uint32_t world, uint32_t lb,
+                       uint64_t* d_counts, void* stream);
+/* Packs (canon, minimizer, source index) by owner. d_cursors[o] must hold the exclusive prefix of the counts. */
+int blight_owner_scatter(const uint64_t* d_canon, const uint32_t* d_mini, uint64_t n, const uint32_t* d_group_cuts,
+                         uint32_t world, uint32_t lb, uint64_t* d_cursors, uint64_t* d_send_canon, uint32_t* d_send_mini,
+                         uint64_t* d_send_src, void* stream);
+/* d_out[d_src[i]] = d_ids_back[i]: ids returned by the owners back into query order. */
+int blight_scatter_ids(const int64_t* d_ids_back, const uint64_t* d_src, uint64_t n, int64_t* d_out, void* stream);
+
 /* Number of kernel launches issued by this library in the calling process (all threads) since load. */
 uint64_t blight_launch_count(void);
 
