@@ -116,16 +116,20 @@ class ClockSampler:
 def build_workload_index(args, rank, world, tmpdir):
     """Rank 0 builds the flat index with the product's host builder and saves it; the others load the blob."""
     from blight_b200 import api, synth
+    if world > 1:
+        import torch.distributed as dist
+        box = [tmpdir]
+        dist.broadcast_object_list(box, src=0)  # every rank must look in rank 0's directory
+        tmpdir = box[0]
     blob = os.path.join(tmpdir, "bench_index.blflat")
     g = synth.random_genome(args.genome, seed=42)
     t0 = time.time()
     if rank == 0:
         st, ln = synth.cut_unitigs(g, args.k, 2000, seed=43)
-        flat = api.FlatIndex.build_spans(g, st, ln, args.k, args.m, args.n, args.s, args.b, threads=0)
-        if world > 1 or True:
-            flat.save(blob)
+        # torchrun exports OMP_NUM_THREADS=1: ask for the host's cores explicitly
+        flat = api.FlatIndex.build_spans(g, st, ln, args.k, args.m, args.n, args.s, args.b, threads=os.cpu_count() or 1)
+        flat.save(blob)
     if world > 1:
-        import torch.distributed as dist
         dist.barrier()
         if rank != 0:
             flat = api.FlatIndex.load(blob)
@@ -145,7 +149,7 @@ def run_reference(args, rank):
     with tempfile.TemporaryDirectory() as td:
         g, flat, blob, _ = build_workload_index(args, 0, 1, td)
         ref = oracle.Reference.from_blob(blob, args.k, args.m)  # reference object holding the identical index
-    threads = ref.max_threads()
+    threads = os.cpu_count() or ref.max_threads()
     n_reads = args.cpu_sample_reads
     rb, ro = synth.simulate_reads(g, n_reads, args.read_len, 0.01, 0.5, seed=44)
     kmers = n_reads * (args.read_len - args.k + 1)
@@ -289,7 +293,7 @@ def main():
                 if not os.path.exists(blob):
                     flat.save(blob)
                 ref = oracle.Reference.from_blob(blob, args.k, args.m)
-                threads = ref.max_threads()
+                threads = os.cpu_count() or ref.max_threads()
                 ref.query_reads(sb[: 2000 * args.read_len], so[:2001], threads=threads, want_ids=False)
                 _, f, nf, sec = ref.query_reads(sb, so, threads=threads, want_ids=False)
                 kind = "reference"

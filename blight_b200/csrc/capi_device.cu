@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <omp.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>

@@ -146,55 +146,61 @@ __device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, u
 	return false;
 }
 
-template <bool SMALL>
-__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini) {
-	const uint4 bd = __ldg(I.bucket + mini);
-	if (bd.z == 0) return -1;
-	const DevMphf* __restrict__ M = I.mphf + (mini >> I.lb);
-	const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(M));  // bits_sector_base, pos_sector_base
-	const uint32_t* bits = I.bits + ((((uint64_t)m0.y << 32) | m0.x) << 3);
+// Descriptors of the bucket a k-mer routes to (all L1/L2 resident).
+struct BucketRef {
+	uint4 bd;                  // start_lo, start_hi, nuc, -
+	const DevMphf* M;
+	uint4 m0;                  // bits_sector_base, pos_sector_base
+	const uint32_t* bits;
+};
 
-	// BBHash levels (bbhash.h:619-639): first level whose bit is set wins
-	uint64_t s0 = 0, s1 = 0;
-	uint32_t w[8];
-	uint32_t r = 0;
-	bool hit = false;
-	if (SMALL) {
-		uint32_t off = 0;
-		#pragma unroll 1
-		for (int level = 0; level < kLevels; level++) {
-			uint64_t h;
-			if (level == 0) h = s0 = hash_bis(x, kSeed0);
-			else if (level == 1) h = s1 = hash_bis(x, kSeed1);
-			else h = xs128_next(s0, s1);
-			const uint32_t dom = __ldg(&M->dom32[level]);
+__device__ __forceinline__ BucketRef load_bucket(const DevIndexView& I, uint32_t mini) {
+	BucketRef B;
+	B.bd = __ldg(I.bucket + mini);
+	B.M = I.mphf + (mini >> I.lb);
+	B.m0 = __ldg(reinterpret_cast<const uint4*>(B.M));
+	B.bits = I.bits + ((((uint64_t)B.m0.y << 32) | B.m0.x) << 3);
+	return B;
+}
+
+// BBHash levels [lv_begin, lv_end) (bbhash.h:619-639): first level whose bit is set wins. (s0, s1) is the hasher state
+// (h0, h1, then xorshift128*), `off` the first bit of level lv_begin; both are carried so the probe can be resumed.
+// On a hit, w holds the sector and r the bit inside its 224-bit chunk.
+template <bool SMALL>
+__device__ __forceinline__ bool probe_levels(const BucketRef& B, uint64_t x, int lv_begin, int lv_end, uint64_t& s0, uint64_t& s1,
+                                             uint64_t& off, uint32_t (&w)[8], uint32_t& r) {
+	#pragma unroll 1
+	for (int level = lv_begin; level < lv_end; level++) {
+		uint64_t h;
+		if (level == 0) h = s0 = hash_bis(x, kSeed0);
+		else if (level == 1) h = s1 = hash_bis(x, kSeed1);
+		else h = xs128_next(s0, s1);
+		if (SMALL) {
+			const uint32_t dom = __ldg(&B.M->dom32[level]);
 			// fastmod64 (bbhash.h:660-662) with a 32-bit domain: hi64(h * dom)
-			const uint32_t bit = off + (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * dom + __umulhi((uint32_t)h, dom)) >> 32);
+			const uint32_t bit = (uint32_t)off + (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * dom + __umulhi((uint32_t)h, dom)) >> 32);
 			const uint32_t chunk = bit / kChunkBits;
 			r = bit - chunk * kChunkBits;
-			ld_bits_sector(bits + ((uint64_t)chunk << 3), w);
-			if ((pick7(w, r >> 5) >> (r & 31)) & 1u) { hit = true; break; }
+			ld_bits_sector(B.bits + ((uint64_t)chunk << 3), w);
 			off += dom;
-		}
-	} else {
-		uint64_t off = 0;
-		#pragma unroll 1
-		for (int level = 0; level < kLevels; level++) {
-			uint64_t h;
-			if (level == 0) h = s0 = hash_bis(x, kSeed0);
-			else if (level == 1) h = s1 = hash_bis(x, kSeed1);
-			else h = xs128_next(s0, s1);
-			const uint64_t dom = __ldg(&M->dom[level]);
+		} else {
+			const uint64_t dom = __ldg(&B.M->dom[level]);
 			const uint64_t bit = off + __umul64hi(h, dom);
 			const uint64_t chunk = bit / kChunkBits;
 			r = (uint32_t)(bit - chunk * kChunkBits);
-			ld_bits_sector(bits + (chunk << 3), w);
-			if ((pick7(w, r >> 5) >> (r & 31)) & 1u) { hit = true; break; }
+			ld_bits_sector(B.bits + (chunk << 3), w);
 			off += dom;
 		}
+		if ((pick7(w, r >> 5) >> (r & 31)) & 1u) return true;
 	}
-	const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(M) + 1);  // id_offset, fb_off
-	const uint4 m2 = __ldg(reinterpret_cast<const uint4*>(M) + 2);  // fb_count, nbits, fields_per_sector, fps_magic
+	return false;
+}
+
+// Everything after the level probe: rank (or fallback map), position, guard, window scan, id.
+__device__ __forceinline__ int64_t finish_lookup(const DevIndexView& I, const BucketRef& B, uint64_t x, bool hit,
+                                                 const uint32_t (&w)[8], uint32_t r) {
+	const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(B.M) + 1);  // id_offset, fb_off
+	const uint4 m2 = __ldg(reinterpret_cast<const uint4*>(B.M) + 2);  // fb_count, nbits, fields_per_sector, fps_magic
 	uint32_t rank;
 	if (hit) {
 		// bitVector::rank (bbhash.h:467-480): ones before this chunk + ones below the bit inside the chunk
@@ -221,19 +227,30 @@ __device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x,
 	uint32_t psec = __umulhi(rank, m2.w);  // floor(rank / fps) or one less
 	uint32_t slot = rank - psec * fps;
 	if (slot >= fps) { slot -= fps; psec++; }
-	const uint32_t* ps = I.pos + (((((uint64_t)m0.w << 32) | m0.z) + psec) << 3);
+	const uint32_t* ps = I.pos + (((((uint64_t)B.m0.w << 32) | B.m0.z) + psec) << 3);
 	const uint32_t o = slot * nbits, ow = o >> 5;
 	uint32_t pw[8];
 	ld_pos_sector(ps, pw);
 	uint32_t field = __funnelshift_r(pick8(pw, ow), pick8(pw, (ow + 1) & 7), o & 31);
 	if (nbits < 32) field &= (1u << nbits) - 1u;
 	const uint32_t pos = field << I.b;
-	if (!((uint64_t)pos + I.k - 1 < (uint64_t)bd.z)) return -1;
-	const uint64_t P = (((uint64_t)bd.y << 32) | bd.x) + pos;
+	if (!((uint64_t)pos + I.k - 1 < (uint64_t)B.bd.z)) return -1;
+	const uint64_t P = (((uint64_t)B.bd.y << 32) | B.bd.x) + pos;
 	const uint64_t rx = rc64(x, I.k);
 	const bool ok = (I.k >= 8 && I.b >= 3) ? scan_windows(I.seq, P, I.k, 1u << I.b, x, rx) : scan_windows_loop(I.seq, P, I.k, 1u << I.b, x, rx);
 	if (!ok) return -1;
 	return (int64_t)((uint64_t)rank + (((uint64_t)m1.y << 32) | m1.x));
+}
+
+template <bool SMALL>
+__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini) {
+	const BucketRef B = load_bucket(I, mini);
+	if (B.bd.z == 0) return -1;
+	uint64_t s0 = 0, s1 = 0, off = 0;
+	uint32_t w[8];
+	uint32_t r = 0;
+	const bool hit = probe_levels<SMALL>(B, x, 0, kLevels, s0, s1, off, w, r);
+	return finish_lookup(I, B, x, hit, w, r);
 }
 
 }  // namespace blight
