@@ -277,7 +277,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": world * total_kmers * e_steps / dt, "unit": "k-mers/s",
-               "h2d_bytes_per_step": int(h_bases.numel() + 2 * 8 * (args.reads + 1)), "d2h_bytes_per_step": 8 * api.N_CTR,
+               "h2d_bytes_per_step": int(h_bases.numel() + 8 * (args.reads + 1)), "d2h_bytes_per_step": 8 * api.N_CTR,
                "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps, "mode": "bool (file_query counters), pinned host reads",
                "found": int(ectr[api.CTR_FOUND]), "not_found": int(ectr[api.CTR_NOT_FOUND])}
 

@@ -161,6 +161,14 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 	cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { blight_index_free(idx); return cuda_fail(e, "cudaStreamCreate"); }
 	idx->host_stream = st;
+	cudaStream_t cs;
+	cudaEvent_t e1, e2;
+	if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess) {
+		blight_index_free(idx);
+		return fail(BL_ERR_CUDA, "cannot create the copy stream of the host entry points");
+	}
+	idx->copy_stream = cs; idx->ev_copy = e1; idx->ev_ws = e2;
 	idx->host_mutex = new std::mutex();
 	DevIndexView& v = idx->v;
 	v.bucket = static_cast<const uint4*>(idx->d_bucket);
@@ -186,6 +194,9 @@ void blight_index_free(blight_index* idx) {
 	cudaFree(idx->d_fbk); cudaFree(idx->d_fbv);
 	for (void* w : idx->ws) cudaFree(w);
 	if (idx->host_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->host_stream));
+	if (idx->copy_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->copy_stream));
+	if (idx->ev_copy) cudaEventDestroy(static_cast<cudaEvent_t>(idx->ev_copy));
+	if (idx->ev_ws) cudaEventDestroy(static_cast<cudaEvent_t>(idx->ev_ws));
 	delete static_cast<std::mutex*>(idx->host_mutex);
 	delete idx;
 }
@@ -276,15 +287,36 @@ int run_host_reads(const blight_index* idx, const char* text, uint64_t len, cons
 		if ((rc = ws_reserve(idx, 4, (n + 1) * 8, &d_koff)) != BL_OK) return rc;
 		if ((rc = ws_reserve(idx, 5, std::max<uint64_t>(total_kmers, 1) * 8, &d_ids)) != BL_OK) return rc;
 	}
-	CU(cudaMemcpyAsync(d_text, text, len, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_beg, beg, (n + 1) * 8, cudaMemcpyHostToDevice, st));
 	if (end) CU(cudaMemcpyAsync(d_end, end, n * 8, cudaMemcpyHostToDevice, st));
 	CU(cudaMemsetAsync(d_ctr, 0, BLIGHT_N_CTR * 8, st));
 	if (ids_out) CU(cudaMemcpyAsync(d_koff, koff, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-	rc = launch_reads(&idx->v, idx->v.k, idx->v.m, static_cast<const char*>(d_text), static_cast<const uint64_t*>(d_beg),
-	                  static_cast<const uint64_t*>(end ? d_end : nullptr), static_cast<const uint64_t*>(d_koff), n, len, nullptr,
-	                  nullptr, static_cast<int64_t*>(d_ids), static_cast<uint64_t*>(d_ctr), st);
-	if (rc != BL_OK) return fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+	// The text goes over in chunks on a second stream; the kernel for chunk c (k-mers starting inside it) waits only
+	// for that chunk (+ a halo), so the copy of chunk c+1 overlaps the lookups of chunk c.
+	cudaStream_t cs = static_cast<cudaStream_t>(idx->copy_stream);
+	uint64_t chunk = 64ull << 20;  // a multiple of kReadsStrip
+	if (const char* e = getenv("BLIGHT_HOST_CHUNK_KB")) {  // tuning / test knob
+		const uint64_t kb = strtoull(e, nullptr, 10);
+		if (kb) chunk = ((kb << 10) + kReadsStrip - 1) / kReadsStrip * kReadsStrip;
+	}
+	const uint64_t halo = kReadsStrip;
+	CU(cudaEventRecord(static_cast<cudaEvent_t>(idx->ev_ws), st));  // the copy must not overtake the previous call's kernels
+	CU(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(idx->ev_ws), 0));
+	uint64_t copied = 0;
+	for (uint64_t c0 = 0; c0 < len; c0 += chunk) {
+		const uint64_t c1 = std::min(len, c0 + chunk);
+		const uint64_t upto = std::min(len, c1 + halo);
+		if (upto > copied) {
+			CU(cudaMemcpyAsync(static_cast<char*>(d_text) + copied, text + copied, upto - copied, cudaMemcpyHostToDevice, cs));
+			copied = upto;
+		}
+		CU(cudaEventRecord(static_cast<cudaEvent_t>(idx->ev_copy), cs));
+		CU(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(idx->ev_copy), 0));
+		rc = launch_reads(&idx->v, idx->v.k, idx->v.m, static_cast<const char*>(d_text), static_cast<const uint64_t*>(d_beg),
+		                  static_cast<const uint64_t*>(end ? d_end : nullptr), static_cast<const uint64_t*>(d_koff), n, len, nullptr,
+		                  nullptr, static_cast<int64_t*>(d_ids), static_cast<uint64_t*>(d_ctr), st, c0, c1);
+		if (rc != BL_OK) return fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+	}
 	if (ids_out && total_kmers) CU(cudaMemcpyAsync(ids_out, d_ids, total_kmers * 8, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(ctr, d_ctr, BLIGHT_N_CTR * 8, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));

@@ -67,6 +67,9 @@ struct blight_index {
 	void* d_bucket = nullptr; void* d_mphf = nullptr; void* d_bits = nullptr; void* d_pos = nullptr; void* d_seq = nullptr;
 	void* d_fbk = nullptr; void* d_fbv = nullptr;
 	void* host_stream = nullptr;  // internal stream of the *_host entry points
+	void* copy_stream = nullptr;  // H2D chunks of a host batch, overlapped with the kernels on host_stream
+	void* ev_copy = nullptr;
+	void* ev_ws = nullptr;
 	void* host_mutex = nullptr;
 	void* ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // grow-only scratch of the *_host entry points
 	size_t ws_cap[6] = {0, 0, 0, 0, 0, 0};

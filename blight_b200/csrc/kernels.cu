@@ -88,7 +88,7 @@ template <int MODE, bool SMALL, int EAGER>
 __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                     const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                     const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
-                                                    bool aligned16, uint64_t* __restrict__ out_canon,
+                                                    uint64_t strip_lo, uint64_t strip_hi, bool aligned16, uint64_t* __restrict__ out_canon,
                                                     uint32_t* __restrict__ out_mini, int64_t* __restrict__ out_ids,
                                                     uint64_t* __restrict__ ctr) {
 	__shared__ uint32_t s_pack[kWarps][kStripWords];  // 2-bit codes, 16 per word, first base in the high bits
@@ -109,14 +109,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 	uint32_t* keys = s_keys[wid];
 	const uint32_t w = k - m + 1;
 	const uint32_t mmask = (1u << (2 * m)) - 1u;
-	const uint64_t n_strips = (total_bases + kStrip - 1) / kStrip;
+	const uint64_t n_strips = strip_hi;  // this launch handles strips [strip_lo, strip_hi) of the buffer
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
 	const double reads_per_base = (double)n_reads / (double)total_bases;
 	uint32_t found = 0, notfound = 0, invalid = 0;
 	uint32_t q_head = 0, q_count = 0;  // warp-uniform
 	const uint32_t qw = kParks ? wid : 0;
 
-	uint64_t strip = (uint64_t)blockIdx.x * kWarps + wid;
+	uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid;
 	uint64_t t0 = 0, r = 0;
 	uint32_t n_pos = 0;
 	int it = 0;
@@ -291,25 +291,27 @@ int eager_levels() {
 
 template <int MODE, bool SMALL, int EAGER>
 void launch_reads_e(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
-                    const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, bool al,
-                    uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream) {
+                    const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
+                    uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
+                    cudaStream_t stream) {
 	static const int per_sm = blocks_per_sm(k_reads<MODE, SMALL, EAGER>);
-	const uint64_t n_strips = (total_bases + kStrip - 1) / kStrip;
+	const uint64_t n_strips = strip_hi - strip_lo;
 	const uint64_t want = (n_strips + kWarps - 1) / kWarps;
 	const uint64_t cap = (uint64_t)sm_count() * per_sm;  // persistent: one resident wave, warps stride over the strips
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
 	k_reads<MODE, SMALL, EAGER><<<grid, kThreads, 0, stream>>>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
-	                                                          al, d_canon, d_mini, d_ids, d_ctr);
+	                                                          strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr);
 }
 
 template <int MODE, bool SMALL>
 void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
-                    const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, bool al,
-                    uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream) {
+                    const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
+                    uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
+                    cudaStream_t stream) {
 	const int e = MODE == kEmitPairs ? 16 : eager_levels();
-	if (e == 2) launch_reads_e<MODE, SMALL, 2>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, al, d_canon, d_mini, d_ids, d_ctr, stream);
-	else if (e == 3) launch_reads_e<MODE, SMALL, 3>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, al, d_canon, d_mini, d_ids, d_ctr, stream);
-	else launch_reads_e<MODE, SMALL, kLevels>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, al, d_canon, d_mini, d_ids, d_ctr, stream);
+	if (e == 2) launch_reads_e<MODE, SMALL, 2>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
+	else if (e == 3) launch_reads_e<MODE, SMALL, 3>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
+	else launch_reads_e<MODE, SMALL, kLevels>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
 }
 
 }  // namespace
@@ -337,12 +339,17 @@ int launch_lookup_kmers(const DevIndexView& I, const uint64_t* d_canon, const ui
 
 int launch_reads(const DevIndexView* I, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
                  const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
-                 uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream) {
+                 uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream, uint64_t pos_begin,
+                 uint64_t pos_end) {
 	if (n_reads == 0 || total_bases == 0) return 0;
+	if (pos_end > total_bases) pos_end = total_bases;
+	if (pos_begin >= pos_end) return 0;
+	if ((pos_begin % kStrip) != 0 || (pos_end < total_bases && (pos_end % kStrip) != 0)) return BLIGHT_ERR_INVALID_ARG;
+	const uint64_t strip_lo = pos_begin / kStrip, strip_hi = (pos_end + kStrip - 1) / kStrip;
 	DevIndexView v{};
 	if (I) v = *I;
 	const bool al = (reinterpret_cast<uintptr_t>(d_bases) & 15) == 0;
-#define BL_ARGS v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, al, d_canon, d_mini, d_ids, d_ctr, stream
+#define BL_ARGS v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream
 	if (!I) launch_reads_t<kEmitPairs, true>(BL_ARGS);
 	else if (d_ids) { if (v.small) launch_reads_t<kLookupIds, true>(BL_ARGS); else launch_reads_t<kLookupIds, false>(BL_ARGS); }
 	else { if (v.small) launch_reads_t<kLookupCount, true>(BL_ARGS); else launch_reads_t<kLookupCount, false>(BL_ARGS); }

@@ -23,8 +23,14 @@ int launch_lookup_kmers(const DevIndexView& I, const uint64_t* d_canon, const ui
 //   I == null          : front end only, (canon, minimizer) pairs to d_canon / d_mini at d_kmer_off[r] + position
 //   I != null, d_ids   : ids to d_ids at d_kmer_off[r] + position, counters accumulated into d_ctr
 //   I != null, !d_ids  : counters only (d_kmer_off unused, may be null)
+// Only k-mers starting in [pos_begin, pos_end) are handled (the buffer must be valid up to pos_end + k - 1), which lets
+// a host batch be copied and queried chunk by chunk.
 int launch_reads(const DevIndexView* I, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
                  const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
-                 uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream);
+                 uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream, uint64_t pos_begin = 0,
+                 uint64_t pos_end = ~0ull);
+
+// Start positions are handled in strips of this many bases; pos_begin of a partial launch must be a multiple of it.
+constexpr uint64_t kReadsStrip = 256;
 
 }  // namespace blight

@@ -167,6 +167,27 @@ def test_ragged_read_lengths(tmp_path, torch_cuda):
     assert int(ctr[0]) == int(wctr[0]) and int(ctr[1]) == int(wctr[1])
 
 
+def test_host_batch_in_many_chunks(tmp_path, torch_cuda, monkeypatch):
+    """The host entry points copy and query a batch chunk by chunk (copy/compute overlap); tiny chunks must give the
+    same ids and counters as one chunk, including reads that straddle chunk boundaries."""
+    g, ub, uo, rb, ro = common.synthetic(400_000, 5000, seed=77, sub_rate=0.02)
+    flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=9, n=7, s=0, b=6, threads=0)
+    port = common.cport_of(flat, tmp_path)
+    idx = flat.upload(0)
+    want, wctr = port.query_reads(rb, ro)
+    for kb in ("1", "7", "100000"):
+        monkeypatch.setenv("BLIGHT_HOST_CHUNK_KB", kb)
+        ids, ctr = idx.query_reads_host(rb, ro)
+        assert np.array_equal(ids, want), kb
+        assert (int(ctr[0]), int(ctr[1]), int(ctr[2])) == (int(wctr[0]), int(wctr[1]), int(wctr[2]))
+        _, ctr2 = idx.query_reads_host(rb, ro, want_ids=False)
+        assert np.array_equal(ctr, ctr2)
+    text = synth.fasta_bytes(rb, ro)
+    monkeypatch.setenv("BLIGHT_HOST_CHUNK_KB", "3")
+    c3 = idx.query_fasta_host(text)
+    assert (int(c3[0]), int(c3[1])) == (int(wctr[0]), int(wctr[1]))
+
+
 def test_large_scale_properties(torch_cuda):
     """5 Mbp index / 1.2 M reads (beyond what the oracle checks in seconds): size-independent properties —
     self-query ids are a bijection on [0, N); a k-mer and its reverse complement get the same id; queries are
