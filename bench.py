@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-sample-reads", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--count-only", action="store_true", help="diagnostic: time the counting (bool) mode instead of the id mode")
     return ap.parse_args()
 
 
@@ -201,6 +202,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     tmpdir = tempfile.mkdtemp(prefix="blight_bench_")
@@ -220,7 +222,10 @@ def main():
     d_ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
 
     def step():
-        idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
+        if args.count_only:
+            idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
+        else:
+            idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -320,7 +325,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_reads<ids>",
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_reads<count>" if args.count_only else "k_reads<ids>",
                          "bytes_per_kmer_algorithmic": balg, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "found_fraction": found_frac, "index": {"number_kmer": info["number_kmer"], "device_bytes": idx.info["device_bytes"],

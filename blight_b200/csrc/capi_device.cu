@@ -181,6 +181,21 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 	v.k = H.k; v.m = H.m; v.b = H.b; v.lb = F.lb();
 	v.kmask = (1ull << (2 * H.k)) - 1;
 	v.small = small;
+	{
+		// per-position "answered found" bitmap: run the lookup core over every window of every bucket, once
+		const size_t vbytes = ((size_t)(H.total_nuc + 31) / 32 + 1) * 4;
+		cudaError_t ve = cudaMalloc(&idx->d_valid, vbytes);
+		if (ve == cudaSuccess) ve = cudaMemset(idx->d_valid, 0, vbytes);
+		if (ve != cudaSuccess) { blight_index_free(idx); return cuda_fail(ve, "cudaMalloc(valid bitmap)"); }
+		int vrc = launch_window_valid(v, H.n_buckets, H.total_nuc, static_cast<uint32_t*>(idx->d_valid), nullptr);
+		ve = cudaDeviceSynchronize();
+		if (vrc != BL_OK || ve != cudaSuccess) {
+			blight_index_free(idx);
+			return fail(BL_ERR_CUDA, std::string("valid-window kernel failed: ") + (ve != cudaSuccess ? cudaGetErrorString(ve) : g_last_cuda_error));
+		}
+		v.valid = static_cast<const uint32_t*>(idx->d_valid);
+		bytes += vbytes;
+	}
 	fill_info(F, &idx->info);
 	idx->info.device_bytes = bytes;
 	*out = idx;
@@ -191,7 +206,7 @@ void blight_index_free(blight_index* idx) {
 	if (!idx) return;
 	DeviceGuard guard(idx->device);
 	cudaFree(idx->d_bucket); cudaFree(idx->d_mphf); cudaFree(idx->d_bits); cudaFree(idx->d_pos); cudaFree(idx->d_seq);
-	cudaFree(idx->d_fbk); cudaFree(idx->d_fbv);
+	cudaFree(idx->d_fbk); cudaFree(idx->d_fbv); cudaFree(idx->d_valid);
 	for (void* w : idx->ws) cudaFree(w);
 	if (idx->host_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->host_stream));
 	if (idx->copy_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->copy_stream));

@@ -16,6 +16,11 @@
 //                  funnel shift of adjacent words (the reference stores one bit per vector<bool> slot,
 //                  blight.cpp:317-318); zero padded past the end for the 2^b-window scan (blight.cpp:732-739).
 //   fallback       sorted (key, rank) arrays for keys no level accommodated (bbhash.h:567-575).
+//   valid          1 bit per base position p of the sequences: does the reference answer "found" when queried with the
+//                  k-mer spelled by the window starting at p, routed to p's own bucket? Computed once at upload by running
+//                  the lookup core itself on every window. It lets a query whose neighbour in the read was found at
+//                  position T check the window at T+-1 and, on a match, skip the position read and the 2^b scan while
+//                  still answering exactly as the reference would (including its junction-window false positives).
 #pragma once
 #include <cstdint>
 
@@ -52,6 +57,7 @@ struct DevIndexView {
 	const uint32_t* seq;
 	const uint64_t* fb_keys;
 	const uint64_t* fb_vals;
+	const uint32_t* valid;  // 1 bit per base position p (bit p&31 of word p>>5): see below
 	uint64_t kmask;
 	uint32_t k, m, b, lb;
 	uint32_t small;  // every MPHF group has fewer than 2^32 level bits: 32-bit bit arithmetic in the probe
@@ -65,7 +71,7 @@ struct blight_index {
 	blight::DevIndexView v{};
 	blight_info info{};
 	void* d_bucket = nullptr; void* d_mphf = nullptr; void* d_bits = nullptr; void* d_pos = nullptr; void* d_seq = nullptr;
-	void* d_fbk = nullptr; void* d_fbv = nullptr;
+	void* d_fbk = nullptr; void* d_fbv = nullptr; void* d_valid = nullptr;
 	void* host_stream = nullptr;  // internal stream of the *_host entry points
 	void* copy_stream = nullptr;  // H2D chunks of a host batch, overlapped with the kernels on host_stream
 	void* ev_copy = nullptr;

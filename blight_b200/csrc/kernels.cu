@@ -48,6 +48,35 @@ __global__ void __launch_bounds__(kThreads) k_lookup_kmers(DevIndexView I, const
 	}
 }
 
+// valid[p] = the reference answers "found" for the k-mer spelled by the window at base position p when the query is
+// routed to p's own bucket (device_index.hpp). One thread per position, one ballot word per warp.
+template <bool SMALL>
+__global__ void __launch_bounds__(kThreads) k_window_valid(DevIndexView I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* __restrict__ valid) {
+	const uint64_t n_round = (total_nuc + 31) & ~31ull;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
+		bool v = false;
+		if (p < total_nuc) {
+			// last bucket whose start is <= p: the non-empty bucket holding p (empty ones share their successor's start)
+			uint64_t lo = 0, hi = n_buckets - 1;
+			while (lo < hi) {
+				const uint64_t mid = (lo + hi + 1) >> 1;
+				const uint4 bd = __ldg(I.bucket + mid);
+				if ((((uint64_t)bd.y << 32) | bd.x) <= p) lo = mid; else hi = mid - 1;
+			}
+			const uint4 bd = __ldg(I.bucket + lo);
+			const uint64_t start = ((uint64_t)bd.y << 32) | bd.x;
+			if (p >= start && p - start < bd.z) {
+				const uint64_t wv = window_at(I.seq, p, I.k);
+				const uint64_t rc = rc64(wv, I.k);
+				v = lookup_one<SMALL>(I, wv < rc ? wv : rc, (uint32_t)lo) >= 0;
+			}
+		}
+		const uint32_t word = __ballot_sync(0xffffffffu, v);
+		if ((threadIdx.x & 31) == 0) valid[p >> 5] = word;
+	}
+}
+
 enum ReadsMode { kEmitPairs = 0, kLookupIds = 1, kLookupCount = 2 };
 
 // first read r in [0, n_reads) with off[r+1] > p, i.e. the read containing base position p (or the gap before it).
@@ -264,6 +293,248 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 	}
 }
 
+// ---- k_reads_sk: the same path, super-k-mer aware ------------------------------------------------------------------
+//
+// Consecutive k-mers of a read that share their minimizer (a super-k-mer, kmer.h:629-693) sit at consecutive positions
+// of one bucket when they are in the graph. Per strip a warp therefore
+//   C1  cuts the strip's k-mers into runs of equal minimizer inside one read,
+//   C2  sends the FIRST k-mer of every run through the whole lookup (one run per lane: a dense batch), keeping where it
+//       matched (T) and on which strand,
+//   C3  checks for every other k-mer of a run the single window at T +- distance: on a match the answer is the
+//       precomputed valid[] bit of that window (device_index.hpp) — no position read, no 2^b scan, and in counting mode
+//       no MPHF probe either; in id mode only the MPHF rank is still needed,
+//   C4  sends what is left (k-mers covering a sequencing error, runs whose first k-mer is absent) through the whole
+//       lookup, compacted into dense batches.
+// Answers are identical to k_reads: a window that equals the query decides "found" exactly as the reference does.
+constexpr int kMaxRuns = 64;  // runs per strip handled through C2/C3; later ones take the plain lookup
+
+__device__ __forceinline__ uint64_t strip_kmer(const uint32_t* pack, uint32_t q, uint32_t k) {
+	const uint32_t wi = q >> 4, s = 2u * (q & 15);
+	const uint32_t a = pack[wi], b = pack[wi + 1], c = pack[wi + 2];
+	return (((uint64_t)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s)) >> (64 - 2 * k);
+}
+
+template <int MODE, bool SMALL>
+__global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
+                                                       const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
+                                                       const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
+                                                       uint64_t strip_lo, uint64_t strip_hi, bool aligned16,
+                                                       int64_t* __restrict__ out_ids, uint64_t* __restrict__ ctr) {
+	__shared__ uint32_t s_pack[kWarps][kStripWords];
+	__shared__ uint32_t s_bad[kWarps][kStripWords];
+	__shared__ uint32_t s_keys[kWarps][kStripKeys];
+	__shared__ uint64_t s_run_T[kWarps][kMaxRuns];   // where the run's first k-mer matched (absolute base position)
+	__shared__ uint64_t s_run_o[MODE == kLookupIds ? kWarps : 1][kMaxRuns];  // output slot of the run's first k-mer
+	__shared__ uint32_t s_run_mn[kWarps][kMaxRuns];  // minimizer of the run
+	__shared__ uint16_t s_run_q[kWarps][kMaxRuns];   // strip position of the run's first k-mer
+	__shared__ uint8_t s_run_flag[kWarps][kMaxRuns]; // bit0: first k-mer found, bit1: text and read on the same strand
+	__shared__ uint8_t s_runid[kWarps][kStrip];      // run of every strip position (0xFF: no k-mer / handled already)
+	__shared__ uint8_t s_resid[kWarps][kStrip];      // positions left for C4
+
+	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t* pack = s_pack[wid];
+	uint32_t* bad = s_bad[wid];
+	uint32_t* keys = s_keys[wid];
+	const uint32_t ow = MODE == kLookupIds ? wid : 0;
+	const uint32_t w = k - m + 1;
+	const uint32_t mmask = (1u << (2 * m)) - 1u;
+	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
+	const double reads_per_base = (double)n_reads / (double)total_bases;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	uint32_t found = 0, notfound = 0, invalid = 0;
+
+	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
+		const uint64_t t0 = strip * kStrip;
+		const uint32_t n_pos = (uint32_t)min((uint64_t)kStrip, total_bases - t0);
+		const uint32_t n_load = (uint32_t)min((uint64_t)(kStrip + 32), total_bases - t0);
+		__syncwarp();
+		// A. pack
+		if (lane < kStripWords) {
+			const uint32_t b0 = lane * 16;
+			uint32_t word = 0, badw = 0;
+			if (b0 < n_load) {
+				unsigned char ch[16];
+				if (aligned16 && b0 + 16 <= n_load) {
+					const uint4 v = __ldcs(reinterpret_cast<const uint4*>(bases + t0 + b0));
+					*reinterpret_cast<uint4*>(ch) = v;
+				} else {
+					#pragma unroll
+					for (int j = 0; j < 16; j++) ch[j] = (b0 + j < n_load) ? (unsigned char)bases[t0 + b0 + j] : (unsigned char)'A';
+				}
+				#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const uint32_t c = nuc_code(ch[j]);
+					badw = (badw << 1) | (c >> 2);
+					word = (word << 2) | (c & 3u);
+				}
+			}
+			pack[lane] = word;
+			bad[lane] = badw;
+		}
+		uint64_t r = 0;
+		if (lane == 0) r = find_read(read_off, n_reads, reads_per_base, t0);
+		r = __shfl_sync(0xffffffffu, r, 0);
+		__syncwarp();
+		// B. m-mer keys
+		for (uint32_t q = lane; q < n_pos + w - 1; q += 32) {
+			const uint32_t wi = q >> 4, s = 2u * (q & 15);
+			const uint32_t v = __funnelshift_l(pack[wi + 1], pack[wi], s) >> (32 - 2 * m);
+			keys[q] = mini_key(parity_canon(v & mmask, m));
+		}
+		__syncwarp();
+
+		// C1. runs of equal minimizer inside one read
+		uint32_t n_runs = 0;
+		bool c_have = false;          // state of the position before this batch (lane 31 of the previous batch)
+		uint32_t c_mn = 0;
+		uint64_t c_rbeg = 0;
+		#pragma unroll 1
+		for (int it = 0; it < kPerLane; it++) {
+			const uint32_t q = it * 32 + lane;
+			bool have = false;
+			uint32_t mn = 0;
+			uint64_t rbeg = 0, o = 0;
+			if (q < n_pos) {
+				const uint64_t p = t0 + q;
+				while (r + 1 < n_reads && __ldg(read_off + r + 1) <= p) r++;
+				rbeg = __ldg(read_off + r);
+				const uint64_t rend = read_end ? __ldg(read_end + r) : __ldg(read_off + r + 1);
+				if (p >= rbeg && p + k <= rend) {
+					const uint32_t wi = q >> 4;
+					const uint64_t bb = ((uint64_t)bad[wi] << 32) | ((uint64_t)bad[wi + 1] << 16) | bad[wi + 2];
+					if ((bb >> (48 - (q & 15) - k)) & ((1ull << k) - 1)) {
+						invalid++;  // nuc2int would throw (kmer.h:56-69)
+					} else {
+						uint32_t best = keys[q];
+						for (uint32_t j = 1; j < w; j++) best = min(best, keys[q + j]);
+						mn = mini_from_key(best);
+						if (MODE == kLookupIds) o = __ldg(kmer_off + r) + (p - rbeg);
+						have = true;
+					}
+				}
+			}
+			bool p_have = __shfl_up_sync(0xffffffffu, have, 1);
+			uint32_t p_mn = __shfl_up_sync(0xffffffffu, mn, 1);
+			uint64_t p_rbeg = __shfl_up_sync(0xffffffffu, rbeg, 1);
+			if (lane == 0) { p_have = c_have; p_mn = c_mn; p_rbeg = c_rbeg; }
+			const bool boundary = have && (!p_have || p_mn != mn || p_rbeg != rbeg);
+			const uint32_t bm = __ballot_sync(0xffffffffu, boundary);
+			const uint32_t id = n_runs + __popc(bm & (lt_mask | (1u << lane))) - 1;  // run this position belongs to
+			uint8_t tag = 0xFF;
+			if (have) {
+				if (id < (uint32_t)kMaxRuns) {
+					tag = (uint8_t)id;
+					if (boundary) {
+						s_run_mn[wid][id] = mn;
+						s_run_q[wid][id] = (uint16_t)q;
+						if (MODE == kLookupIds) s_run_o[ow][id] = o;
+					}
+				} else {
+					// more runs than the table holds: plain lookup, right away
+					const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
+					const int64_t idr = lookup_one<SMALL>(I, f < rc ? f : rc, mn);
+					if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + o), (long long)idr);
+					if (idr >= 0) found++; else notfound++;
+				}
+			}
+			if (q < kStrip) s_runid[wid][q] = tag;
+			n_runs += __popc(bm);
+			c_have = __shfl_sync(0xffffffffu, have, 31);
+			c_mn = __shfl_sync(0xffffffffu, mn, 31);
+			c_rbeg = __shfl_sync(0xffffffffu, rbeg, 31);
+		}
+		__syncwarp();
+
+		// C2. the first k-mer of every run: the whole lookup, one run per lane
+		const uint32_t n_anch = n_runs < (uint32_t)kMaxRuns ? n_runs : (uint32_t)kMaxRuns;
+		#pragma unroll 1
+		for (uint32_t base = 0; base < n_anch; base += 32) {
+			const uint32_t id = base + lane;
+			if (id < n_anch) {
+				const uint32_t q = s_run_q[wid][id];
+				const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
+				uint64_t T = 0;
+				const int64_t idr = lookup_one<SMALL>(I, f < rc ? f : rc, s_run_mn[wid][id], &T);
+				uint8_t flag = 0;
+				if (idr >= 0) {
+					flag = 1 | (window_at(I.seq, T, k) == f ? 2 : 0);
+					found++;
+				} else {
+					notfound++;
+				}
+				s_run_T[wid][id] = T;
+				s_run_flag[wid][id] = flag;
+				if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id]), (long long)idr);
+			}
+		}
+		__syncwarp();
+
+		// C3. every other k-mer of a run: one window, next to where the first one matched
+		uint32_t n_res = 0;
+		#pragma unroll 1
+		for (int it = 0; it < kPerLane; it++) {
+			const uint32_t q = it * 32 + lane;
+			const uint32_t id = s_runid[wid][q];
+			bool left = false;
+			if (id < (uint32_t)kMaxRuns && q != s_run_q[wid][id]) {
+				left = true;
+				const uint32_t flag = s_run_flag[wid][id];
+				if (flag & 1) {
+					const uint32_t d = q - s_run_q[wid][id];
+					const uint64_t Ta = s_run_T[wid][id];
+					const BucketRef B = load_bucket(I, s_run_mn[wid][id]);
+					const uint64_t bstart = ((uint64_t)B.bd.y << 32) | B.bd.x;
+					const bool same = flag & 2;
+					const uint64_t Tp = same ? Ta + d : Ta - d;
+					if ((same || Ta >= bstart + d) && Tp >= bstart && Tp - bstart < B.bd.z) {
+						const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
+						if (window_at(I.seq, Tp, k) == (same ? f : rc)) {
+							// the query equals this window, so the reference's answer is the window's valid bit
+							left = false;
+							const bool v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
+							int64_t idr = -1;
+							if (v) { found++; if (MODE == kLookupIds) idr = id_of_found<SMALL>(I, B, f < rc ? f : rc); }
+							else notfound++;
+							if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + d), (long long)idr);
+						}
+					}
+				}
+			}
+			const uint32_t lm = __ballot_sync(0xffffffffu, left);
+			if (left) s_resid[wid][n_res + __popc(lm & lt_mask)] = (uint8_t)q;
+			n_res += __popc(lm);
+		}
+		__syncwarp();
+
+		// C4. the rest: the whole lookup, compacted
+		#pragma unroll 1
+		for (uint32_t base = 0; base < n_res; base += 32) {
+			const uint32_t i = base + lane;
+			if (i < n_res) {
+				const uint32_t q = s_resid[wid][i];
+				const uint32_t id = s_runid[wid][q];
+				const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
+				const int64_t idr = lookup_one<SMALL>(I, f < rc ? f : rc, s_run_mn[wid][id]);
+				if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + (q - s_run_q[wid][id])), (long long)idr);
+				if (idr >= 0) found++; else notfound++;
+			}
+		}
+	}
+
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		found += __shfl_xor_sync(0xffffffffu, found, o);
+		notfound += __shfl_xor_sync(0xffffffffu, notfound, o);
+		invalid += __shfl_xor_sync(0xffffffffu, invalid, o);
+	}
+	if (lane == 0) {
+		if (found) atomicAdd((unsigned long long*)&ctr[BLIGHT_CTR_FOUND], (unsigned long long)found);
+		if (notfound) atomicAdd((unsigned long long*)&ctr[BLIGHT_CTR_NOT_FOUND], (unsigned long long)notfound);
+		if (found + notfound) atomicAdd((unsigned long long*)&ctr[BLIGHT_CTR_QUERIES], (unsigned long long)found + notfound);
+		if (invalid) atomicAdd((unsigned long long*)&ctr[BLIGHT_CTR_INVALID], (unsigned long long)invalid);
+	}
+}
+
 int check(cudaError_t e) { return e == cudaSuccess ? 0 : BLIGHT_ERR_CUDA; }
 
 int sm_count() {
@@ -303,11 +574,37 @@ void launch_reads_e(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
 	                                                          strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr);
 }
 
+bool use_superkmer_kernel() {
+	static const bool v = [] {
+		const char* e = getenv("BLIGHT_READS_KERNEL");  // "plain": per-k-mer lookups only; default: super-k-mer aware
+		return !(e && e[0] == 'p');
+	}();
+	return v;
+}
+
+template <int MODE, bool SMALL>
+void launch_reads_sk(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
+                     const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
+                     uint64_t strip_lo, uint64_t strip_hi, bool al, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream) {
+	static const int per_sm = blocks_per_sm(k_reads_sk<MODE, SMALL>);
+	const uint64_t n_strips = strip_hi - strip_lo;
+	const uint64_t want = (n_strips + kWarps - 1) / kWarps;
+	const uint64_t cap = (uint64_t)sm_count() * per_sm;
+	const unsigned grid = (unsigned)(want < cap ? want : cap);
+	k_reads_sk<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
+	                                                      strip_lo, strip_hi, al, d_ids, d_ctr);
+}
+
 template <int MODE, bool SMALL>
 void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
                     const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
                     uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
                     cudaStream_t stream) {
+	if (MODE != kEmitPairs && v.valid && use_superkmer_kernel()) {
+		launch_reads_sk<MODE == kEmitPairs ? kLookupCount : MODE, SMALL>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
+		                                                                strip_lo, strip_hi, al, d_ids, d_ctr, stream);
+		return;
+	}
 	const int e = MODE == kEmitPairs ? 16 : eager_levels();
 	if (e == 2) launch_reads_e<MODE, SMALL, 2>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
 	else if (e == 3) launch_reads_e<MODE, SMALL, 3>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
@@ -317,6 +614,19 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
 }  // namespace
 
 const char* g_last_cuda_error = "";
+
+int launch_window_valid(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, cudaStream_t stream) {
+	if (total_nuc == 0) return 0;
+	const uint64_t want = (total_nuc + kThreads - 1) / kThreads;
+	const uint64_t cap = (uint64_t)sm_count() * 8;
+	const unsigned grid = (unsigned)(want < cap ? want : cap);
+	if (I.small) k_window_valid<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid);
+	else k_window_valid<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid);
+	g_launches++;
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) g_last_cuda_error = cudaGetErrorString(e);
+	return check(e);
+}
 
 int launch_lookup_kmers(const DevIndexView& I, const uint64_t* d_canon, const uint32_t* d_mini, uint64_t n, int64_t* d_ids,
                         cudaStream_t stream) {

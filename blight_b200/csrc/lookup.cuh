@@ -53,8 +53,9 @@ __device__ __forceinline__ uint32_t pick7(const uint32_t (&w)[8], uint32_t j) {
 
 // Reference loop form of the 2^b-window scan (blight.cpp:730-739): slide one base at a time. Used for k < 8 or b < 3.
 // canon(window) == x  <=>  window == x or window == rx, because x is canonical (x <= rx).
-__device__ __noinline__ bool scan_windows_loop(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
-                                               uint64_t x, uint64_t rx) {
+// Returns the index of a matching window, or -1.
+__device__ __noinline__ int32_t scan_windows_loop(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
+                                                  uint64_t x, uint64_t rx) {
 	const uint64_t wi = P >> 4;
 	const uint32_t s = 2u * (uint32_t)(P & 15);
 	const uint32_t* q = seq + wi;
@@ -70,20 +71,24 @@ __device__ __noinline__ bool scan_windows_loop(const uint32_t* __restrict__ seq,
 			prev = nxt;
 		}
 		const uint64_t w = (((uint64_t)top_hi << 32) | top_lo) >> sh;
-		if (w == x || w == rx) return true;
+		if (w == x || w == rx) return (int32_t)j;
 		top_hi = __funnelshift_l(top_lo, top_hi, 2);
 		top_lo = __funnelshift_l(feed, top_lo, 2);
 		feed <<= 2;
 	}
-	return false;
+	return -1;
 }
 
-// window j of the sequence starting at base P equals x or rx? (three L1-resident word loads)
-__device__ __forceinline__ bool window_matches(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint64_t x, uint64_t rx) {
+// the k bases of the packed sequence starting at base P (three word loads)
+__device__ __forceinline__ uint64_t window_at(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k) {
 	const uint32_t* q = seq + (P >> 4);
 	const uint32_t s = 2u * (uint32_t)(P & 15);
 	const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-	const uint64_t w = ((((uint64_t)__funnelshift_l(b, a, s)) << 32) | __funnelshift_l(c, b, s)) >> (64 - 2 * k);
+	return ((((uint64_t)__funnelshift_l(b, a, s)) << 32) | __funnelshift_l(c, b, s)) >> (64 - 2 * k);
+}
+
+__device__ __forceinline__ bool window_matches(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint64_t x, uint64_t rx) {
+	const uint64_t w = window_at(seq, P, k);
 	return w == x || w == rx;
 }
 
@@ -91,8 +96,8 @@ __device__ __forceinline__ bool window_matches(const uint32_t* __restrict__ seq,
 // compared against the first 8 bases of x and of rx with half-word SIMD compares (HSET2); windows are handled in 8 residue
 // classes (start offset mod 8), so that in the text shifted by the class offset every candidate prefix is half-word
 // aligned. Survivors (the true match, plus ~2^-16 false candidates per window) are verified in full.
-// Requires k >= 8 and nwin >= 8 (a power of two).
-__device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
+// Requires k >= 8 and nwin >= 8 (a power of two). Returns the index of a matching window, or -1.
+__device__ __forceinline__ int32_t scan_windows(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
                                              uint64_t x, uint64_t rx) {
 	const uint32_t* q = seq + (P >> 4);
 	const uint32_t s = 2u * (uint32_t)(P & 15);
@@ -139,11 +144,11 @@ __device__ __forceinline__ bool scan_windows(const uint32_t* __restrict__ seq, u
 				acc &= ~(1u << bit);
 				const uint32_t h = bit >= 16 ? 0u : 1u, bb = bit & 15u;
 				const uint32_t j = (bb & 7u) + 8u * (2u * (2u * half + (bb >> 3)) + h);
-				if (window_matches(seq, P + base + j, k, x, rx)) return true;
+				if (window_matches(seq, P + base + j, k, x, rx)) return (int32_t)(base + j);
 			}
 		}
 	}
-	return false;
+	return -1;
 }
 
 // Descriptors of the bucket a k-mer routes to (all L1/L2 resident).
@@ -196,32 +201,41 @@ __device__ __forceinline__ bool probe_levels(const BucketRef& B, uint64_t x, int
 	return false;
 }
 
+// rank of a key that hit bit r of the sector w (bitVector::rank, bbhash.h:467-480): ones before this chunk + ones
+// below the bit inside the chunk
+__device__ __forceinline__ uint32_t rank_in_sector(const uint32_t (&w)[8], uint32_t r) {
+	const uint32_t j = r >> 5, bi = r & 31;
+	uint32_t rank = w[7];
+	#pragma unroll
+	for (int i = 0; i < 7; i++) {
+		const uint32_t below = (i < (int)j) ? 0xFFFFFFFFu : ((i == (int)j) ? ((1u << bi) - 1u) : 0u);
+		rank += __popc(w[i] & below);
+	}
+	return rank;
+}
+
+// fallback map (bbhash.h:567-575), sorted by key: rank of x, or false
+__device__ __forceinline__ bool fallback_rank(const DevIndexView& I, const uint4& m1, const uint4& m2, uint64_t x, uint32_t& rank) {
+	const uint64_t fb_off = ((uint64_t)m1.w << 32) | m1.z;
+	uint32_t lo = 0, hi = m2.x;
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (__ldg(I.fb_keys + fb_off + mid) < x) lo = mid + 1; else hi = mid;
+	}
+	if (lo >= m2.x || __ldg(I.fb_keys + fb_off + lo) != x) return false;
+	rank = (uint32_t)__ldg(I.fb_vals + fb_off + lo);
+	return true;
+}
+
 // Everything after the level probe: rank (or fallback map), position, guard, window scan, id.
+// T_out receives the absolute base position of the window that matched (when the result is >= 0).
 __device__ __forceinline__ int64_t finish_lookup(const DevIndexView& I, const BucketRef& B, uint64_t x, bool hit,
-                                                 const uint32_t (&w)[8], uint32_t r) {
+                                                 const uint32_t (&w)[8], uint32_t r, uint64_t* T_out = nullptr) {
 	const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(B.M) + 1);  // id_offset, fb_off
 	const uint4 m2 = __ldg(reinterpret_cast<const uint4*>(B.M) + 2);  // fb_count, nbits, fields_per_sector, fps_magic
 	uint32_t rank;
-	if (hit) {
-		// bitVector::rank (bbhash.h:467-480): ones before this chunk + ones below the bit inside the chunk
-		const uint32_t j = r >> 5, bi = r & 31;
-		rank = w[7];
-		#pragma unroll
-		for (int i = 0; i < 7; i++) {
-			const uint32_t below = (i < (int)j) ? 0xFFFFFFFFu : ((i == (int)j) ? ((1u << bi) - 1u) : 0u);
-			rank += __popc(w[i] & below);
-		}
-	} else {
-		// fallback map (bbhash.h:567-575), sorted by key
-		const uint64_t fb_off = ((uint64_t)m1.w << 32) | m1.z;
-		uint32_t lo = 0, hi = m2.x;
-		while (lo < hi) {
-			const uint32_t mid = (lo + hi) >> 1;
-			if (__ldg(I.fb_keys + fb_off + mid) < x) lo = mid + 1; else hi = mid;
-		}
-		if (lo >= m2.x || __ldg(I.fb_keys + fb_off + lo) != x) return -1;
-		rank = (uint32_t)__ldg(I.fb_vals + fb_off + lo);
-	}
+	if (hit) rank = rank_in_sector(w, r);
+	else if (!fallback_rank(I, m1, m2, x, rank)) return -1;
 	// position field (blight.cpp:473-482): uint32 arithmetic, << b
 	const uint32_t nbits = m2.y, fps = m2.z;
 	uint32_t psec = __umulhi(rank, m2.w);  // floor(rank / fps) or one less
@@ -237,20 +251,39 @@ __device__ __forceinline__ int64_t finish_lookup(const DevIndexView& I, const Bu
 	if (!((uint64_t)pos + I.k - 1 < (uint64_t)B.bd.z)) return -1;
 	const uint64_t P = (((uint64_t)B.bd.y << 32) | B.bd.x) + pos;
 	const uint64_t rx = rc64(x, I.k);
-	const bool ok = (I.k >= 8 && I.b >= 3) ? scan_windows(I.seq, P, I.k, 1u << I.b, x, rx) : scan_windows_loop(I.seq, P, I.k, 1u << I.b, x, rx);
-	if (!ok) return -1;
+	const int32_t j = (I.k >= 8 && I.b >= 3) ? scan_windows(I.seq, P, I.k, 1u << I.b, x, rx) : scan_windows_loop(I.seq, P, I.k, 1u << I.b, x, rx);
+	if (j < 0) return -1;
+	if (T_out) *T_out = P + (uint32_t)j;
+	return (int64_t)((uint64_t)rank + (((uint64_t)m1.y << 32) | m1.x));
+}
+
+// Identifier of a key for which the answer "found" is already established (see DevIndexView::valid): only the MPHF
+// rank is needed, no position read and no window scan.
+template <bool SMALL>
+__device__ __forceinline__ int64_t id_of_found(const DevIndexView& I, const BucketRef& B, uint64_t x) {
+	uint64_t s0 = 0, s1 = 0, off = 0;
+	uint32_t w[8];
+	uint32_t r = 0;
+	const bool hit = probe_levels<SMALL>(B, x, 0, kLevels, s0, s1, off, w, r);
+	const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(B.M) + 1);
+	uint32_t rank;
+	if (hit) rank = rank_in_sector(w, r);
+	else {
+		const uint4 m2 = __ldg(reinterpret_cast<const uint4*>(B.M) + 2);
+		if (!fallback_rank(I, m1, m2, x, rank)) return -1;  // cannot happen for a key the reference finds
+	}
 	return (int64_t)((uint64_t)rank + (((uint64_t)m1.y << 32) | m1.x));
 }
 
 template <bool SMALL>
-__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini) {
+__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini, uint64_t* T_out = nullptr) {
 	const BucketRef B = load_bucket(I, mini);
 	if (B.bd.z == 0) return -1;
 	uint64_t s0 = 0, s1 = 0, off = 0;
 	uint32_t w[8];
 	uint32_t r = 0;
 	const bool hit = probe_levels<SMALL>(B, x, 0, kLevels, s0, s1, off, w, r);
-	return finish_lookup(I, B, x, hit, w, r);
+	return finish_lookup(I, B, x, hit, w, r, T_out);
 }
 
 }  // namespace blight
