@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--cpu-sample-reads", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--count-only", action="store_true", help="diagnostic: time the counting (bool) mode instead of the id mode")
+    ap.add_argument("--ids-only", action="store_true", help="diagnostic: time only the id (hash) mode")
+    ap.add_argument("--count-only", action="store_true", help="diagnostic: time only the counting (bool) mode")
     return ap.parse_args()
 
 
@@ -59,6 +60,11 @@ def b_alg(b: int, k: int = 31) -> float:
     + 1.25 B of ASCII in + 8 B id out."""
     seq_sectors = -(-2 * (k + (1 << b) - 1) // 256)
     return 32.0 * (1.65 + 1 + 1 + seq_sectors) + 1.25 + 8.0
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this exact
+# workload (profiles/r01_v5_sk_count_ncu.txt, profiles/r01_v3_kreads_ncu.txt); None for any other configuration.
+NCU_TRAFFIC_BYTES = {"k_reads_sk<count>": 99.76e9, "k_reads<ids>": 209.1e9}
 
 
 def measured_peak():
@@ -177,11 +183,11 @@ def run_reference(args, rank):
 def workload_config(args, world):
     return {
         "workload": f"synthetic {args.genome / 1e6:g} Mbp random-genome unitig graph ({args.genome - args.k + 1} {args.k}-mers) replicated per GPU, "
-                    f"{args.reads} simulated {args.read_len} bp reads per GPU per step (1% subst., 50% revcomp), hash mode (int64 ids)",
+                    f"{args.reads} simulated {args.read_len} bp reads per GPU per step (1% subst., 50% revcomp), file_query semantics (found / not-found counts; the id mode is reported under ids_mode)",
         "k": args.k, "m": args.m, "n": args.n, "s": args.s, "b": args.b,
         "kmers_per_step_per_gpu": args.reads * (args.read_len - args.k + 1),
         "parallelism": f"replica x{world}, reads sharded, no data-path collective",
-        "cache": "inputs (1.5 GB reads + 9.6 GB ids per step) and index exceed the 126 MB L2; no explicit flush",
+        "cache": "inputs (1.5 GB of reads per step) and the index (349 MB) exceed the 126 MB L2; no explicit flush",
     }
 
 
@@ -221,11 +227,11 @@ def main():
     d_ids = torch.empty(total_kmers, dtype=torch.int64, device=dev)
     d_ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
 
-    def step():
-        if args.count_only:
-            idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
-        else:
-            idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
+    def step_count():
+        idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
+
+    def step_ids():
+        idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -233,30 +239,41 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
-    d_ctr.zero_()
+    def timed(step):
+        """W untimed warm-up steps, then K steps between CUDA events on the launching stream; max over ranks."""
+        for _ in range(max(args.warmup, 3)):
+            step()
+        sync_all()
+        d_ctr.zero_()
+        sync_all()
+        l0 = api.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        sync_all()
+        launches = api.launch_count() - l0
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, d_ctr.cpu().numpy().copy()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    sync_all()
-    l0 = api.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync_all()
-    launches = api.launch_count() - l0
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    # headline: file_query semantics (query_sequence_bool over the batch -> Good / Erroneous counters, blight.cpp:780-789)
+    ms, launches, ctr = (0.0, 0, None)
+    if not args.ids_only:
+        ms, launches, ctr = timed(step_count)
+    # the identifier mode (query_sequence_hash: one int64 id per k-mer, blight.cpp:575-591)
+    ids_ms, ids_launches, ids_ctr = (0.0, 0, None)
+    if not args.count_only:
+        ids_ms, ids_launches, ids_ctr = timed(step_ids)
+    if args.ids_only:
+        ms, launches, ctr = ids_ms, ids_launches, ids_ctr
     clocks = sampler.stop() if rank == 0 else None
-    ctr = d_ctr.cpu().numpy()
     found_frac = float(ctr[api.CTR_FOUND]) / max(1.0, float(ctr[api.CTR_QUERIES]))
     value = world * total_kmers * args.steps / (ms * 1e-3)
 
@@ -269,8 +286,9 @@ def main():
         h_roff.copy_(d_roff)
         torch.cuda.synchronize()
         hb, hr = h_bases.numpy(), h_roff.numpy().view(np.uint64)
-        e_steps = max(2, min(args.steps, 3))
-        idx.query_reads_host(hb, hr, want_ids=False)  # warm-up
+        e_steps = args.steps
+        for _ in range(2):
+            idx.query_reads_host(hb, hr, want_ids=False)  # warm-up (sizes the library's device workspace)
         sync_all()
         t0 = time.perf_counter()
         for _ in range(e_steps):
@@ -317,17 +335,25 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        balg = b_alg(args.b, args.k)
-        kernel_ms = ms / args.steps  # the step is exactly one launch of k_reads<ids> per GPU
+        headline_ids = args.ids_only
+        balg = b_alg(args.b, args.k) - (0.0 if headline_ids else 8.0 - 0.125)  # counters instead of an int64 id per k-mer
+        kernel_ms = ms / args.steps  # the step is exactly one launch of the read kernel per GPU
         achieved = balg * total_kmers / (kernel_ms * 1e-3) / 1e9
+        kname = "k_reads<ids>" if headline_ids else "k_reads_sk<count>"
+        default_cfg = (args.genome, args.reads, args.read_len, args.k, args.m, args.n, args.b) == (100_000_000, 10_000_000, 150, 31, 7, 5, 6)
+        traffic = NCU_TRAFFIC_BYTES.get(kname) if default_cfg else None
         line = {
             "metric": "queried k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_reads<count>" if args.count_only else "k_reads<ids>",
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
+                         "algorithmic_bytes_per_launch": balg * total_kmers, "peak_source": peak_src, "kernel": kname,
                          "bytes_per_kmer_algorithmic": balg, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "ids_mode": None if (args.count_only or args.ids_only) else {
+                "value": world * total_kmers * args.steps / (ids_ms * 1e-3), "unit": "k-mers/s", "ms_per_step": ids_ms / args.steps,
+                "kernel": "k_reads<ids>", "note": "query_sequence_hash semantics: one int64 id per k-mer written to HBM (9.6 GB per step)"},
             "found_fraction": found_frac, "index": {"number_kmer": info["number_kmer"], "device_bytes": idx.info["device_bytes"],
                                                      "build_seconds": build_s},
         }

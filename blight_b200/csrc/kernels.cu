@@ -574,12 +574,16 @@ void launch_reads_e(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
 	                                                          strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr);
 }
 
-bool use_superkmer_kernel() {
-	static const bool v = [] {
-		const char* e = getenv("BLIGHT_READS_KERNEL");  // "plain": per-k-mer lookups only; default: super-k-mer aware
-		return !(e && e[0] == 'p');
+// Which read kernel serves a mode. Measured on B200 (100 M-k-mer index, b=6): counting mode 1.88e10 k-mers/s with the
+// super-k-mer kernel vs 1.33e10 plain; id mode 1.25e10 vs 1.31e10 (every k-mer still needs its MPHF rank, so the
+// prediction saves less than its bookkeeping costs). BLIGHT_READS_KERNEL=plain|sk overrides (tuning / tests).
+bool use_superkmer_kernel(bool want_ids) {
+	static const int forced = [] {
+		const char* e = getenv("BLIGHT_READS_KERNEL");
+		return !e ? 0 : (e[0] == 'p' ? 1 : (e[0] == 's' ? 2 : 0));
 	}();
-	return v;
+	if (forced) return forced == 2;
+	return !want_ids;
 }
 
 template <int MODE, bool SMALL>
@@ -600,7 +604,7 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
                     const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
                     uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
                     cudaStream_t stream) {
-	if (MODE != kEmitPairs && v.valid && use_superkmer_kernel()) {
+	if (MODE != kEmitPairs && v.valid && use_superkmer_kernel(MODE == kLookupIds)) {
 		launch_reads_sk<MODE == kEmitPairs ? kLookupCount : MODE, SMALL>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
 		                                                                strip_lo, strip_hi, al, d_ids, d_ctr, stream);
 		return;

@@ -102,6 +102,40 @@ def test_fresh_reads_vs_oracle(shape, tmp_path, torch_cuda):
     assert np.array_equal(idx.query_kmers_host(absent), port.query_kmers(absent))
 
 
+def test_both_read_kernels_agree(tmp_path, torch_cuda):
+    """The per-k-mer kernel and the super-k-mer kernel (anchor + one-window prediction through the valid bitmap) are
+    selected per mode; forced either way (fresh processes, the choice is read once) they must both reproduce the
+    oracle, ids and counters, including on reads with many errors and on an index with b=8."""
+    import subprocess, sys, json as _json
+    code = r"""
+import sys, os, json, numpy as np
+sys.path.insert(0, os.getcwd())
+from blight_b200 import api
+from tests import common
+import oracle, tempfile
+out = {}
+for (m, n, b, sub) in [(7, 5, 6, 0.02), (9, 9, 8, 0.05), (11, 6, 3, 0.0)]:
+    g, ub, uo, rb, ro = common.synthetic(500_000, 5000, seed=5 + m, sub_rate=sub)
+    flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=m, n=n, s=0, b=b, threads=0)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "x.blflat"); flat.save(p); port = oracle.CPort(p)
+        want, wctr = port.query_reads(rb, ro)
+    idx = flat.upload(0)
+    ids, ctr = idx.query_reads_host(rb, ro)
+    _, ctr2 = idx.query_reads_host(rb, ro, want_ids=False)
+    out[f"{m}_{n}_{b}"] = [bool(np.array_equal(ids, want)), [int(c) for c in ctr[:3]] == [int(c) for c in wctr[:3]],
+                           [int(c) for c in ctr2[:3]] == [int(c) for c in wctr[:3]]]
+print(json.dumps(out))
+"""
+    for kern in ("plain", "sk"):
+        env = dict(os.environ, BLIGHT_READS_KERNEL=kern)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stderr[-2000:]
+        res = _json.loads(r.stdout.strip().splitlines()[-1])
+        assert all(all(v) for v in res.values()), (kern, res)
+
+
 def test_other_k(tmp_path, torch_cuda):
     """k != 31 (k=21 m=7, k=16 m=5, k=25 m=11)."""
     for k, m, n, b in [(21, 7, 4, 4), (16, 5, 3, 2), (25, 11, 8, 6)]:
