@@ -339,7 +339,7 @@ def main():
         balg = b_alg(args.b, args.k) - (0.0 if headline_ids else 8.0 - 0.125)  # counters instead of an int64 id per k-mer
         kernel_ms = ms / args.steps  # the step is exactly one launch of the read kernel per GPU
         achieved = balg * total_kmers / (kernel_ms * 1e-3) / 1e9
-        kname = "k_reads<ids>" if headline_ids else "k_reads_sk<count>"
+        kname = "k_reads_sk<ids>" if headline_ids else "k_reads_sk<count>"
         default_cfg = (args.genome, args.reads, args.read_len, args.k, args.m, args.n, args.b) == (100_000_000, 10_000_000, 150, 31, 7, 5, 6)
         traffic = NCU_TRAFFIC_BYTES.get(kname) if default_cfg else None
         line = {
@@ -353,7 +353,7 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "ids_mode": None if (args.count_only or args.ids_only) else {
                 "value": world * total_kmers * args.steps / (ids_ms * 1e-3), "unit": "k-mers/s", "ms_per_step": ids_ms / args.steps,
-                "kernel": "k_reads<ids>", "note": "query_sequence_hash semantics: one int64 id per k-mer written to HBM (9.6 GB per step)"},
+                "kernel": "k_reads_sk<ids>", "note": "query_sequence_hash semantics: one int64 id per k-mer written to HBM (9.6 GB per step)"},
             "found_fraction": found_frac, "index": {"number_kmer": info["number_kmer"], "device_bytes": idx.info["device_bytes"],
                                                      "build_seconds": build_s},
         }

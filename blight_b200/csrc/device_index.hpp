@@ -21,6 +21,14 @@
 //                  the lookup core itself on every window. It lets a query whose neighbour in the read was found at
 //                  position T check the window at T+-1 and, on a match, skip the position read and the 2^b scan while
 //                  still answering exactly as the reference would (including its junction-window false positives).
+//   pos_id         (optional, N < 2^32-1) 1 x u32 per base position p: the identifier the reference returns for the k-mer
+//                  spelled by the window at p (0xFFFFFFFF when it answers -1), computed by the same pass as `valid`. The
+//                  k-mers of a super-k-mer sit at consecutive positions, so the ids of a run are ONE or two sectors
+//                  instead of (levels + rank) sectors per k-mer.
+//   filter         register-blocked Bloom filter over V = {canonical k-mers spelled by the valid windows} (every k-mer the
+//                  reference answers "found" is in V: it matched a window, and that window's valid bit is its own
+//                  answer). One 32-byte sector per key, one probe bit in each of its 8 words. No false negatives, so a
+//                  miss proves "-1" with a single sector read; a hit (true or false positive) takes the whole lookup.
 #pragma once
 #include <cstdint>
 
@@ -32,6 +40,7 @@
 namespace blight {
 
 constexpr uint32_t kChunkBits = 224;  // level bits per 32-byte sector
+constexpr uint32_t kFlagFilterAnchors = 1u;  // first k-mers of runs go through the filter too
 
 struct alignas(64) DevMphf {
 	uint64_t bits_sector_base;  // first sector of this group's level bits (index into DevIndexView::bits, in sectors)
@@ -57,7 +66,11 @@ struct DevIndexView {
 	const uint32_t* seq;
 	const uint64_t* fb_keys;
 	const uint64_t* fb_vals;
-	const uint32_t* valid;  // 1 bit per base position p (bit p&31 of word p>>5): see below
+	const uint32_t* valid;  // 1 bit per base position p (bit p&31 of word p>>5): see above
+	const uint32_t* pos_id; // identifier per base position (0xFFFFFFFF: -1), or null
+	const uint32_t* filter; // 8 words per block, or null
+	uint32_t filter_blocks;
+	uint32_t flags;         // kFlagFilterAnchors
 	uint64_t kmask;
 	uint32_t k, m, b, lb;
 	uint32_t small;  // every MPHF group has fewer than 2^32 level bits: 32-bit bit arithmetic in the probe
@@ -71,7 +84,7 @@ struct blight_index {
 	blight::DevIndexView v{};
 	blight_info info{};
 	void* d_bucket = nullptr; void* d_mphf = nullptr; void* d_bits = nullptr; void* d_pos = nullptr; void* d_seq = nullptr;
-	void* d_fbk = nullptr; void* d_fbv = nullptr; void* d_valid = nullptr;
+	void* d_fbk = nullptr; void* d_fbv = nullptr; void* d_valid = nullptr; void* d_pos_id = nullptr; void* d_filter = nullptr;
 	void* host_stream = nullptr;  // internal stream of the *_host entry points
 	void* copy_stream = nullptr;  // H2D chunks of a host batch, overlapped with the kernels on host_stream
 	void* ev_copy = nullptr;

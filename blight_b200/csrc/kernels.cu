@@ -50,12 +50,15 @@ __global__ void __launch_bounds__(kThreads) k_lookup_kmers(DevIndexView I, const
 
 // valid[p] = the reference answers "found" for the k-mer spelled by the window at base position p when the query is
 // routed to p's own bucket (device_index.hpp). One thread per position, one ballot word per warp.
+// The same pass fills pos_id[p] (the identifier itself) and inserts the k-mers of valid windows into the filter.
 template <bool SMALL>
-__global__ void __launch_bounds__(kThreads) k_window_valid(DevIndexView I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* __restrict__ valid) {
+__global__ void __launch_bounds__(kThreads) k_window_valid(DevIndexView I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* __restrict__ valid,
+                                                           uint32_t* __restrict__ pos_id, uint32_t* __restrict__ filter, uint32_t filter_blocks) {
 	const uint64_t n_round = (total_nuc + 31) & ~31ull;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
 		bool v = false;
+		int64_t id = -1;
 		if (p < total_nuc) {
 			// last bucket whose start is <= p: the non-empty bucket holding p (empty ones share their successor's start)
 			uint64_t lo = 0, hi = n_buckets - 1;
@@ -69,8 +72,12 @@ __global__ void __launch_bounds__(kThreads) k_window_valid(DevIndexView I, uint6
 			if (p >= start && p - start < bd.z) {
 				const uint64_t wv = window_at(I.seq, p, I.k);
 				const uint64_t rc = rc64(wv, I.k);
-				v = lookup_one<SMALL>(I, wv < rc ? wv : rc, (uint32_t)lo) >= 0;
+				const uint64_t x = wv < rc ? wv : rc;
+				id = lookup_one<SMALL>(I, x, (uint32_t)lo);
+				v = id >= 0;
+				if (v && filter) filter_insert(filter, filter_blocks, x);
 			}
+			if (pos_id) pos_id[p] = v ? (uint32_t)id : 0xFFFFFFFFu;
 		}
 		const uint32_t word = __ballot_sync(0xffffffffu, v);
 		if ((threadIdx.x & 31) == 0) valid[p >> 5] = word;
@@ -341,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
 	const double reads_per_base = (double)n_reads / (double)total_bases;
 	const uint32_t lt_mask = (1u << lane) - 1u;
+	const bool filter_anchors = I.filter && (I.flags & kFlagFilterAnchors);
 	uint32_t found = 0, notfound = 0, invalid = 0;
 
 	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
@@ -454,7 +462,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 				const uint32_t q = s_run_q[wid][id];
 				const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
 				uint64_t T = 0;
-				const int64_t idr = lookup_one<SMALL>(I, f < rc ? f : rc, s_run_mn[wid][id], &T);
+				const uint64_t x = f < rc ? f : rc;
+				const int64_t idr = (filter_anchors && !filter_maybe(I, x)) ? -1 : lookup_one<SMALL>(I, x, s_run_mn[wid][id], &T);
 				uint8_t flag = 0;
 				if (idr >= 0) {
 					flag = 1 | (window_at(I.seq, T, k) == f ? 2 : 0);
@@ -491,10 +500,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 						if (window_at(I.seq, Tp, k) == (same ? f : rc)) {
 							// the query equals this window, so the reference's answer is the window's valid bit
 							left = false;
-							const bool v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
+							bool v;
 							int64_t idr = -1;
-							if (v) { found++; if (MODE == kLookupIds) idr = id_of_found<SMALL>(I, B, f < rc ? f : rc); }
-							else notfound++;
+							if (MODE == kLookupIds && I.pos_id) {
+								const uint32_t pid = __ldg(I.pos_id + Tp);
+								v = pid != 0xFFFFFFFFu;
+								if (v) idr = (int64_t)pid;
+							} else {
+								v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
+								if (v && MODE == kLookupIds) idr = id_of_found<SMALL>(I, B, f < rc ? f : rc);
+							}
+							if (v) found++; else notfound++;
 							if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + d), (long long)idr);
 						}
 					}
@@ -506,7 +522,37 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 		}
 		__syncwarp();
 
-		// C4. the rest: the whole lookup, compacted
+		// C4a. the rest, through the negative filter first: most of them cover a sequencing error and are in no bucket,
+		// which one filter sector proves; what passes is compacted again (in place: slots are rewritten only after
+		// the batch that held them was read)
+		if (I.filter) {
+			uint32_t n_keep = 0;
+			#pragma unroll 1
+			for (uint32_t base = 0; base < n_res; base += 32) {
+				const uint32_t i = base + lane;
+				bool keep = false;
+				uint32_t q = 0;
+				if (i < n_res) {
+					q = s_resid[wid][i];
+					const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
+					keep = filter_maybe(I, f < rc ? f : rc);
+					if (!keep) {
+						notfound++;
+						if (MODE == kLookupIds) {
+							const uint32_t id = s_runid[wid][q];
+							__stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + (q - s_run_q[wid][id])), -1ll);
+						}
+					}
+				}
+				const uint32_t km = __ballot_sync(0xffffffffu, keep);
+				__syncwarp();
+				if (keep) s_resid[wid][n_keep + __popc(km & lt_mask)] = (uint8_t)q;
+				n_keep += __popc(km);
+			}
+			n_res = n_keep;
+			__syncwarp();
+		}
+		// C4b. the whole lookup, compacted
 		#pragma unroll 1
 		for (uint32_t base = 0; base < n_res; base += 32) {
 			const uint32_t i = base + lane;
@@ -577,13 +623,13 @@ void launch_reads_e(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
 // Which read kernel serves a mode. Measured on B200 (100 M-k-mer index, b=6): counting mode 1.88e10 k-mers/s with the
 // super-k-mer kernel vs 1.33e10 plain; id mode 1.25e10 vs 1.31e10 (every k-mer still needs its MPHF rank, so the
 // prediction saves less than its bookkeeping costs). BLIGHT_READS_KERNEL=plain|sk overrides (tuning / tests).
-bool use_superkmer_kernel(bool want_ids) {
+bool use_superkmer_kernel(bool want_ids, bool has_pos_id) {
 	static const int forced = [] {
 		const char* e = getenv("BLIGHT_READS_KERNEL");
 		return !e ? 0 : (e[0] == 'p' ? 1 : (e[0] == 's' ? 2 : 0));
 	}();
 	if (forced) return forced == 2;
-	return !want_ids;
+	return !want_ids || has_pos_id;
 }
 
 template <int MODE, bool SMALL>
@@ -604,7 +650,7 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
                     const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
                     uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
                     cudaStream_t stream) {
-	if (MODE != kEmitPairs && v.valid && use_superkmer_kernel(MODE == kLookupIds)) {
+	if (MODE != kEmitPairs && v.valid && use_superkmer_kernel(MODE == kLookupIds, v.pos_id != nullptr)) {
 		launch_reads_sk<MODE == kEmitPairs ? kLookupCount : MODE, SMALL>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
 		                                                                strip_lo, strip_hi, al, d_ids, d_ctr, stream);
 		return;
@@ -619,13 +665,14 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
 
 const char* g_last_cuda_error = "";
 
-int launch_window_valid(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, cudaStream_t stream) {
+int launch_window_valid(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, uint32_t* d_pos_id,
+                        uint32_t* d_filter, uint32_t filter_blocks, cudaStream_t stream) {
 	if (total_nuc == 0) return 0;
 	const uint64_t want = (total_nuc + kThreads - 1) / kThreads;
 	const uint64_t cap = (uint64_t)sm_count() * 8;
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
-	if (I.small) k_window_valid<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid);
-	else k_window_valid<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid);
+	if (I.small) k_window_valid<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks);
+	else k_window_valid<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks);
 	g_launches++;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) g_last_cuda_error = cudaGetErrorString(e);

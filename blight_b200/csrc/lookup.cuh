@@ -35,6 +35,13 @@ __device__ __forceinline__ void ld_pos_sector(const uint32_t* p, uint32_t (&w)[8
 	             : "l"(p));
 }
 
+// one filter block: default L2 policy, not worth an L1 line
+__device__ __forceinline__ void ld_filter_sector(const uint32_t* p, uint32_t (&w)[8]) {
+	asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+	             : "l"(p));
+}
+
 // word j (0..7) of a sector held in registers
 __device__ __forceinline__ uint32_t pick8(const uint32_t (&w)[8], uint32_t j) {
 	const bool b0 = j & 1, b1 = j & 2, b2 = j & 4;
@@ -273,6 +280,38 @@ __device__ __forceinline__ int64_t id_of_found(const DevIndexView& I, const Buck
 		if (!fallback_rank(I, m1, m2, x, rank)) return -1;  // cannot happen for a key the reference finds
 	}
 	return (int64_t)((uint64_t)rank + (((uint64_t)m1.y << 32) | m1.x));
+}
+
+// ---- the negative filter (device_index.hpp: `filter`) ----------------------------------------------------------------
+// block = hi32(h) scaled to the block count, bit i of the key = 5 bits of a second product, one per word of the block.
+__device__ __forceinline__ uint64_t filter_hash(uint64_t x) {
+	x ^= x >> 31; x *= 0x9E3779B97F4A7C15ull;
+	x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull;
+	x ^= x >> 32;
+	return x;
+}
+__device__ __forceinline__ uint64_t filter_bits(uint64_t h) { return (h * 0xD6E8FEB86659FD93ull) >> 24; }  // 40 bits
+
+// false: x is certainly not in V, the reference answers -1. true: unknown.
+__device__ __forceinline__ bool filter_maybe(const DevIndexView& I, uint64_t x) {
+	const uint64_t h = filter_hash(x);
+	const uint32_t blk = __umulhi((uint32_t)(h >> 32), I.filter_blocks);
+	const uint64_t g = filter_bits(h);
+	uint32_t w[8];
+	ld_filter_sector(I.filter + ((uint64_t)blk << 3), w);
+	uint32_t ok = 1;
+	#pragma unroll
+	for (int i = 0; i < 8; i++) ok &= w[i] >> ((uint32_t)(g >> (5 * i)) & 31u);
+	return ok & 1u;
+}
+
+__device__ __forceinline__ void filter_insert(uint32_t* filter, uint32_t filter_blocks, uint64_t x) {
+	const uint64_t h = filter_hash(x);
+	const uint32_t blk = __umulhi((uint32_t)(h >> 32), filter_blocks);
+	const uint64_t g = filter_bits(h);
+	uint32_t* p = filter + ((uint64_t)blk << 3);
+	#pragma unroll
+	for (int i = 0; i < 8; i++) atomicOr(p + i, 1u << ((uint32_t)(g >> (5 * i)) & 31u));
 }
 
 template <bool SMALL>

@@ -103,9 +103,10 @@ def test_fresh_reads_vs_oracle(shape, tmp_path, torch_cuda):
 
 
 def test_both_read_kernels_agree(tmp_path, torch_cuda):
-    """The per-k-mer kernel and the super-k-mer kernel (anchor + one-window prediction through the valid bitmap) are
-    selected per mode; forced either way (fresh processes, the choice is read once) they must both reproduce the
-    oracle, ids and counters, including on reads with many errors and on an index with b=8."""
+    """The per-k-mer kernel and the super-k-mer kernel (anchor + one-window prediction through the valid bitmap / the
+    position->id table, negative filter in front of the residual lookups) forced either way and with each optional
+    table switched off (fresh processes, the knobs are read once): all must reproduce the oracle, ids and counters,
+    including on reads with many errors and on an index with b=8."""
     import subprocess, sys, json as _json
     code = r"""
 import sys, os, json, numpy as np
@@ -127,8 +128,15 @@ for (m, n, b, sub) in [(7, 5, 6, 0.02), (9, 9, 8, 0.05), (11, 6, 3, 0.0)]:
                            [int(c) for c in ctr2[:3]] == [int(c) for c in wctr[:3]]]
 print(json.dumps(out))
 """
-    for kern in ("plain", "sk"):
-        env = dict(os.environ, BLIGHT_READS_KERNEL=kern)
+    variants = [
+        {"BLIGHT_READS_KERNEL": "plain"},
+        {"BLIGHT_READS_KERNEL": "sk"},                                                   # + position->id table + filter
+        {"BLIGHT_READS_KERNEL": "sk", "BLIGHT_POS_ID": "0", "BLIGHT_FILTER_BITS": "0"},  # valid bitmap only
+        {"BLIGHT_READS_KERNEL": "sk", "BLIGHT_FILTER_BITS": "3"},                        # many filter false positives
+        {"BLIGHT_READS_KERNEL": "sk", "BLIGHT_FILTER_ANCHORS": "0", "BLIGHT_POS_ID": "0"},
+    ]
+    for kern in variants:
+        env = dict(os.environ, **kern)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         assert r.returncode == 0, r.stderr[-2000:]
