@@ -304,22 +304,48 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 //
 // Consecutive k-mers of a read that share their minimizer (a super-k-mer, kmer.h:629-693) sit at consecutive positions
 // of one bucket when they are in the graph. Per strip a warp therefore
-//   C1  cuts the strip's k-mers into runs of equal minimizer inside one read,
+//   C1  cuts the strip's k-mers into runs of equal minimizer inside one read (a lane owns 8 consecutive positions: the
+//       window minimum is rolled over them, the read bookkeeping is amortised),
 //   C2  sends the FIRST k-mer of every run through the whole lookup (one run per lane: a dense batch), keeping where it
-//       matched (T) and on which strand,
-//   C3  checks for every other k-mer of a run the single window at T +- distance: on a match the answer is the
-//       precomputed valid[] bit of that window (device_index.hpp) — no position read, no 2^b scan, and in counting mode
-//       no MPHF probe either; in id mode only the MPHF rank is still needed,
-//   C4  sends what is left (k-mers covering a sequencing error, runs whose first k-mer is absent) through the whole
-//       lookup, compacted into dense batches.
+//       matched (T), on which strand, and how far the bucket extends from there,
+//   C3  checks for every other k-mer of a run the single window at T +- distance: on a match the answer is what the
+//       reference answers for that window — the precomputed valid[] bit, or in id mode the pos_id[] entry
+//       (device_index.hpp): no MPHF probe, no position read, no 2^b scan,
+//   C4  sends what is left (k-mers covering a sequencing error, runs whose first k-mer is absent) through the negative
+//       filter (one sector proves "-1" for the ones in no bucket) and the survivors through the whole lookup, compacted
+//       into dense batches.
+// C2 and C4 share ONE inlined copy of the lookup core (two turns of the same loop): the kernel must stay inside the
+// 32 KB instruction cache, warps sit at unrelated program counters (the v6 profile lost 20 % of its issue slots to
+// instruction fetch).
 // Answers are identical to k_reads: a window that equals the query decides "found" exactly as the reference does.
-constexpr int kMaxRuns = 64;  // runs per strip handled through C2/C3; later ones take the plain lookup
+constexpr int kMaxRuns = 64;                              // runs per strip handled through C2/C3
+constexpr uint32_t kTagNone = 0xFF, kTagOverflow = 0xFE;  // s_runid: no k-mer here / run table full: plain lookup
+constexpr int kKeySlots = kStripKeys + kStripKeys / 8 + 8;
+
+__device__ __forceinline__ uint32_t kidx(uint32_t q) { return q + (q >> 3); }  // one pad word per 8 keys: a lane walks 8 consecutive keys
 
 __device__ __forceinline__ uint64_t strip_kmer(const uint32_t* pack, uint32_t q, uint32_t k) {
 	const uint32_t wi = q >> 4, s = 2u * (q & 15);
 	const uint32_t a = pack[wi], b = pack[wi + 1], c = pack[wi + 2];
 	return (((uint64_t)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s)) >> (64 - 2 * k);
 }
+
+// read bookkeeping of one lane while it walks consecutive positions
+struct ReadCursor {
+	uint64_t r, beg, next, end;
+	__device__ __forceinline__ void load(const uint64_t* __restrict__ off, const uint64_t* __restrict__ endp) {
+		beg = __ldg(off + r);
+		next = __ldg(off + r + 1);
+		end = endp ? __ldg(endp + r) : next;
+	}
+	// moves to the read containing p (or the gap before it); true if the read changed
+	__device__ __forceinline__ bool seek(const uint64_t* __restrict__ off, const uint64_t* __restrict__ endp, uint64_t n_reads, uint64_t p) {
+		if (p < next || r + 1 >= n_reads) return false;
+		do { r++; next = __ldg(off + r + 1); } while (p >= next && r + 1 < n_reads);
+		load(off, endp);
+		return true;
+	}
+};
 
 template <int MODE, bool SMALL>
 __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
@@ -329,19 +355,21 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
                                                        int64_t* __restrict__ out_ids, uint64_t* __restrict__ ctr) {
 	__shared__ uint32_t s_pack[kWarps][kStripWords];
 	__shared__ uint32_t s_bad[kWarps][kStripWords];
-	__shared__ uint32_t s_keys[kWarps][kStripKeys];
+	__shared__ uint32_t s_keys[kWarps][kKeySlots];   // key of position q at kidx(q)
 	__shared__ uint64_t s_run_T[kWarps][kMaxRuns];   // where the run's first k-mer matched (absolute base position)
 	__shared__ uint64_t s_run_o[MODE == kLookupIds ? kWarps : 1][kMaxRuns];  // output slot of the run's first k-mer
 	__shared__ uint32_t s_run_mn[kWarps][kMaxRuns];  // minimizer of the run
 	__shared__ uint16_t s_run_q[kWarps][kMaxRuns];   // strip position of the run's first k-mer
+	__shared__ uint16_t s_run_dmax[kWarps][kMaxRuns];// largest distance whose predicted window still starts inside the bucket
 	__shared__ uint8_t s_run_flag[kWarps][kMaxRuns]; // bit0: first k-mer found, bit1: text and read on the same strand
-	__shared__ uint8_t s_runid[kWarps][kStrip];      // run of every strip position (0xFF: no k-mer / handled already)
+	__shared__ uint64_t s_runid8[kWarps][kStrip / 8];// run of every strip position, one byte each
 	__shared__ uint8_t s_resid[kWarps][kStrip];      // positions left for C4
 
 	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	uint32_t* pack = s_pack[wid];
 	uint32_t* bad = s_bad[wid];
 	uint32_t* keys = s_keys[wid];
+	uint8_t* runid = reinterpret_cast<uint8_t*>(s_runid8[wid]);
 	const uint32_t ow = MODE == kLookupIds ? wid : 0;
 	const uint32_t w = k - m + 1;
 	const uint32_t mmask = (1u << (2 * m)) - 1u;
@@ -349,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 	const double reads_per_base = (double)n_reads / (double)total_bases;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const bool filter_anchors = I.filter && (I.flags & kFlagFilterAnchors);
+	const uint64_t kones = (1ull << k) - 1;  // k <= 31
 	uint32_t found = 0, notfound = 0, invalid = 0;
 
 	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
@@ -379,191 +408,245 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 			pack[lane] = word;
 			bad[lane] = badw;
 		}
-		uint64_t r = 0;
-		if (lane == 0) r = find_read(read_off, n_reads, reads_per_base, t0);
-		r = __shfl_sync(0xffffffffu, r, 0);
+		ReadCursor rc_;
+		rc_.r = 0;
+		if (lane == 0) rc_.r = find_read(read_off, n_reads, reads_per_base, t0);
+		rc_.r = __shfl_sync(0xffffffffu, rc_.r, 0);
 		__syncwarp();
 		// B. m-mer keys
 		for (uint32_t q = lane; q < n_pos + w - 1; q += 32) {
 			const uint32_t wi = q >> 4, s = 2u * (q & 15);
 			const uint32_t v = __funnelshift_l(pack[wi + 1], pack[wi], s) >> (32 - 2 * m);
-			keys[q] = mini_key(parity_canon(v & mmask, m));
+			keys[kidx(q)] = mini_key(parity_canon(v & mmask, m));
 		}
 		__syncwarp();
 
-		// C1. runs of equal minimizer inside one read
-		uint32_t n_runs = 0;
-		bool c_have = false;          // state of the position before this batch (lane 31 of the previous batch)
-		uint32_t c_mn = 0;
-		uint64_t c_rbeg = 0;
-		#pragma unroll 1
-		for (int it = 0; it < kPerLane; it++) {
-			const uint32_t q = it * 32 + lane;
-			bool have = false;
-			uint32_t mn = 0;
-			uint64_t rbeg = 0, o = 0;
-			if (q < n_pos) {
-				const uint64_t p = t0 + q;
-				while (r + 1 < n_reads && __ldg(read_off + r + 1) <= p) r++;
-				rbeg = __ldg(read_off + r);
-				const uint64_t rend = read_end ? __ldg(read_end + r) : __ldg(read_off + r + 1);
-				if (p >= rbeg && p + k <= rend) {
-					const uint32_t wi = q >> 4;
-					const uint64_t bb = ((uint64_t)bad[wi] << 32) | ((uint64_t)bad[wi + 1] << 16) | bad[wi + 2];
-					if ((bb >> (48 - (q & 15) - k)) & ((1ull << k) - 1)) {
-						invalid++;  // nuc2int would throw (kmer.h:56-69)
-					} else {
-						uint32_t best = keys[q];
-						for (uint32_t j = 1; j < w; j++) best = min(best, keys[q + j]);
-						mn = mini_from_key(best);
-						if (MODE == kLookupIds) o = __ldg(kmer_off + r) + (p - rbeg);
-						have = true;
-					}
-				}
-			}
-			bool p_have = __shfl_up_sync(0xffffffffu, have, 1);
-			uint32_t p_mn = __shfl_up_sync(0xffffffffu, mn, 1);
-			uint64_t p_rbeg = __shfl_up_sync(0xffffffffu, rbeg, 1);
-			if (lane == 0) { p_have = c_have; p_mn = c_mn; p_rbeg = c_rbeg; }
-			const bool boundary = have && (!p_have || p_mn != mn || p_rbeg != rbeg);
-			const uint32_t bm = __ballot_sync(0xffffffffu, boundary);
-			const uint32_t id = n_runs + __popc(bm & (lt_mask | (1u << lane))) - 1;  // run this position belongs to
-			uint8_t tag = 0xFF;
-			if (have) {
-				if (id < (uint32_t)kMaxRuns) {
-					tag = (uint8_t)id;
-					if (boundary) {
-						s_run_mn[wid][id] = mn;
-						s_run_q[wid][id] = (uint16_t)q;
-						if (MODE == kLookupIds) s_run_o[ow][id] = o;
-					}
-				} else {
-					// more runs than the table holds: plain lookup, right away
-					const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
-					const int64_t idr = lookup_one<SMALL>(I, f < rc ? f : rc, mn);
-					if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + o), (long long)idr);
-					if (idr >= 0) found++; else notfound++;
-				}
-			}
-			if (q < kStrip) s_runid[wid][q] = tag;
-			n_runs += __popc(bm);
-			c_have = __shfl_sync(0xffffffffu, have, 31);
-			c_mn = __shfl_sync(0xffffffffu, mn, 31);
-			c_rbeg = __shfl_sync(0xffffffffu, rbeg, 31);
+		// C1. runs of equal minimizer inside one read; lane L owns positions 8L .. 8L+7
+		const uint32_t q0 = lane * 8;
+		uint32_t kmin[8];  // window minimum (as key) of each owned position
+		{
+			const uint32_t* kp = keys + 9 * lane;  // kidx(q0 + e) = 9 L + e + (e >> 3)
+			// w >= 8 (the launcher sends smaller windows to k_reads):
+			// window j = keys [j, j + w) = (suffix of [j, 7)) + common [7, w) + (prefix of [w, w + j))
+			uint32_t common = kp[7];
+			for (uint32_t e = 8; e < w; e++) common = min(common, kp[e + (e >> 3)]);
+			kmin[7] = common;
+			uint32_t sfx = 0xFFFFFFFFu;
+			#pragma unroll
+			for (int j = 6; j >= 0; j--) { sfx = min(sfx, kp[j]); kmin[j] = min(common, sfx); }
+			uint32_t pfx = 0xFFFFFFFFu;
+			const uint32_t* kw = kp + w - 1;
+			const uint32_t wl = (w - 1) & 7;  // kidx is not linear: position w - 1 + j sits at w - 1 + j + ((w - 1 + j) >> 3)
+			#pragma unroll
+			for (int j = 1; j < 8; j++) { pfx = min(pfx, kw[j + ((w - 1) >> 3) + ((wl + j) >> 3)]); kmin[j] = min(kmin[j], pfx); }
 		}
-		__syncwarp();
-
-		// C2. the first k-mer of every run: the whole lookup, one run per lane
-		const uint32_t n_anch = n_runs < (uint32_t)kMaxRuns ? n_runs : (uint32_t)kMaxRuns;
-		#pragma unroll 1
-		for (uint32_t base = 0; base < n_anch; base += 32) {
-			const uint32_t id = base + lane;
-			if (id < n_anch) {
-				const uint32_t q = s_run_q[wid][id];
-				const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
-				uint64_t T = 0;
-				const uint64_t x = f < rc ? f : rc;
-				const int64_t idr = (filter_anchors && !filter_maybe(I, x)) ? -1 : lookup_one<SMALL>(I, x, s_run_mn[wid][id], &T);
-				uint8_t flag = 0;
-				if (idr >= 0) {
-					flag = 1 | (window_at(I.seq, T, k) == f ? 2 : 0);
-					found++;
-				} else {
-					notfound++;
-				}
-				s_run_T[wid][id] = T;
-				s_run_flag[wid][id] = flag;
-				if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id]), (long long)idr);
-			}
-		}
-		__syncwarp();
-
-		// C3. every other k-mer of a run: one window, next to where the first one matched
-		uint32_t n_res = 0;
-		#pragma unroll 1
-		for (int it = 0; it < kPerLane; it++) {
-			const uint32_t q = it * 32 + lane;
-			const uint32_t id = s_runid[wid][q];
-			bool left = false;
-			if (id < (uint32_t)kMaxRuns && q != s_run_q[wid][id]) {
-				left = true;
-				const uint32_t flag = s_run_flag[wid][id];
-				if (flag & 1) {
-					const uint32_t d = q - s_run_q[wid][id];
-					const uint64_t Ta = s_run_T[wid][id];
-					const BucketRef B = load_bucket(I, s_run_mn[wid][id]);
-					const uint64_t bstart = ((uint64_t)B.bd.y << 32) | B.bd.x;
-					const bool same = flag & 2;
-					const uint64_t Tp = same ? Ta + d : Ta - d;
-					if ((same || Ta >= bstart + d) && Tp >= bstart && Tp - bstart < B.bd.z) {
-						const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
-						if (window_at(I.seq, Tp, k) == (same ? f : rc)) {
-							// the query equals this window, so the reference's answer is the window's valid bit
-							left = false;
-							bool v;
-							int64_t idr = -1;
-							if (MODE == kLookupIds && I.pos_id) {
-								const uint32_t pid = __ldg(I.pos_id + Tp);
-								v = pid != 0xFFFFFFFFu;
-								if (v) idr = (int64_t)pid;
-							} else {
-								v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
-								if (v && MODE == kLookupIds) idr = id_of_found<SMALL>(I, B, f < rc ? f : rc);
-							}
-							if (v) found++; else notfound++;
-							if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + d), (long long)idr);
-						}
-					}
-				}
-			}
-			const uint32_t lm = __ballot_sync(0xffffffffu, left);
-			if (left) s_resid[wid][n_res + __popc(lm & lt_mask)] = (uint8_t)q;
-			n_res += __popc(lm);
-		}
-		__syncwarp();
-
-		// C4a. the rest, through the negative filter first: most of them cover a sequencing error and are in no bucket,
-		// which one filter sector proves; what passes is compacted again (in place: slots are rewritten only after
-		// the batch that held them was read)
-		if (I.filter) {
-			uint32_t n_keep = 0;
+		// which owned positions start a k-mer, and where reads change
+		const uint64_t p0 = t0 + q0;
+		while (rc_.r + 1 < n_reads && __ldg(read_off + rc_.r + 1) <= p0) rc_.r++;
+		rc_.load(read_off, read_end);
+		const uint32_t r_first = (uint32_t)rc_.r;
+		uint32_t have = 0, newread = 0;
+		{
+			const uint32_t wi = q0 >> 4, o16 = q0 & 15;
+			const uint64_t bb = ((uint64_t)bad[wi] << 48) | ((uint64_t)bad[wi + 1] << 32) | ((uint64_t)bad[wi + 2] << 16) | bad[wi + 3];
 			#pragma unroll 1
-			for (uint32_t base = 0; base < n_res; base += 32) {
-				const uint32_t i = base + lane;
-				bool keep = false;
-				uint32_t q = 0;
-				if (i < n_res) {
-					q = s_resid[wid][i];
-					const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
-					keep = filter_maybe(I, f < rc ? f : rc);
-					if (!keep) {
-						notfound++;
-						if (MODE == kLookupIds) {
-							const uint32_t id = s_runid[wid][q];
-							__stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + (q - s_run_q[wid][id])), -1ll);
+			for (int j = 0; j < 8; j++) {
+				const uint64_t p = p0 + j;
+				if (j && rc_.seek(read_off, read_end, n_reads, p)) newread |= 1u << j;
+				if (q0 + j < n_pos && p >= rc_.beg && p + k <= rc_.end) {
+					// nuc2int rejects any byte outside ACGTacgt (kmer.h:56-69); only bases of queried k-mers are ever looked at
+					if ((bb >> (64 - o16 - j - k)) & kones) invalid++;
+					else have |= 1u << j;
+				}
+			}
+		}
+		const uint32_t r_last = (uint32_t)rc_.r;
+		// run starts: a k-mer whose predecessor is missing, in another read, or has another minimizer
+		uint32_t p_have = __shfl_up_sync(0xffffffffu, have >> 7, 1);
+		const uint32_t p_key = __shfl_up_sync(0xffffffffu, kmin[7], 1);
+		const uint32_t p_r = __shfl_up_sync(0xffffffffu, r_last, 1);
+		if (lane == 0) p_have = 0;
+		uint32_t bnd = 0;
+		if ((have & 1u) && (!p_have || p_key != kmin[0] || p_r != r_first)) bnd = 1u;
+		#pragma unroll
+		for (int j = 1; j < 8; j++)
+			if (((have >> j) & 1u) && (!((have >> (j - 1)) & 1u) || kmin[j] != kmin[j - 1] || ((newread >> j) & 1u))) bnd |= 1u << j;
+		uint32_t incl = __popc(bnd);
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= (uint32_t)o) incl += t;
+		}
+		const uint32_t n_runs = __shfl_sync(0xffffffffu, incl, 31);
+		const uint32_t run_base = incl - __popc(bnd);
+		{
+			// run records (the minimizer is filled in by C2) and the run of every owned position
+			ReadCursor c2;
+			c2.r = 0; c2.beg = c2.next = c2.end = 0;
+			if (MODE == kLookupIds) {
+				c2.r = rc_.r - (r_last - r_first);
+				c2.load(read_off, read_end);
+			}
+			uint32_t id = run_base;
+			#pragma unroll 1
+			for (uint32_t bm = bnd; bm && id < (uint32_t)kMaxRuns; bm &= bm - 1, id++) {
+				const uint32_t j = __ffs(bm) - 1;
+				s_run_q[wid][id] = (uint16_t)(q0 + j);
+				if (MODE == kLookupIds) {
+					c2.seek(read_off, read_end, n_reads, p0 + j);
+					s_run_o[ow][id] = __ldg(kmer_off + c2.r) + (p0 + j - c2.beg);
+				}
+			}
+			uint64_t tags = 0;
+			#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				uint32_t tag = kTagNone;
+				if ((have >> j) & 1u) {
+					const uint32_t rid = run_base + __popc(bnd & ((2u << j) - 1u)) - 1u;  // the first k-mer of a strip always starts a run
+					tag = rid < (uint32_t)kMaxRuns ? rid : kTagOverflow;
+				}
+				tags |= (uint64_t)tag << (8 * j);
+			}
+			s_runid8[wid][lane] = tags;
+		}
+		__syncwarp();
+		uint32_t n_res = 0;
+		if (n_runs > (uint32_t)kMaxRuns) {
+			// more runs than the table holds (many tiny reads): those k-mers take the plain lookup in C4
+			#pragma unroll 1
+			for (int it = 0; it < kPerLane; it++) {
+				const uint32_t q = it * 32 + lane;
+				const bool ov = runid[q] == kTagOverflow;
+				const uint32_t om = __ballot_sync(0xffffffffu, ov);
+				if (ov) s_resid[wid][n_res + __popc(om & lt_mask)] = (uint8_t)q;
+				n_res += __popc(om);
+			}
+		}
+		const uint32_t n_anch = n_runs < (uint32_t)kMaxRuns ? n_runs : (uint32_t)kMaxRuns;
+
+		#pragma unroll 1
+		for (int phase = 0; phase < 2; phase++) {
+			if (phase == 1) {
+				// C3. every other k-mer of a run: one window, next to where the first one matched
+				#pragma unroll 1
+				for (int it = 0; it < kPerLane; it++) {
+					const uint32_t q = it * 32 + lane;
+					const uint32_t id = runid[q];
+					bool left = false;
+					if (id < (uint32_t)kMaxRuns && q != s_run_q[wid][id]) {
+						left = true;
+						const uint32_t flag = s_run_flag[wid][id];
+						const uint32_t d = q - s_run_q[wid][id];
+						if ((flag & 1) && d <= s_run_dmax[wid][id]) {
+							const bool same = flag & 2;
+							const uint64_t Ta = s_run_T[wid][id];
+							const uint64_t Tp = same ? Ta + d : Ta - d;
+							const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
+							if (window_at(I.seq, Tp, k) == (same ? f : rc)) {
+								// the query equals this window, so the reference's answer is the window's own
+								left = false;
+								bool v;
+								int64_t idr = -1;
+								if (MODE == kLookupIds && I.pos_id) {
+									const uint32_t pid = __ldg(I.pos_id + Tp);
+									v = pid != 0xFFFFFFFFu;
+									if (v) idr = (int64_t)pid;
+								} else {
+									v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
+									if (v && MODE == kLookupIds) idr = id_of_found<SMALL>(I, load_bucket(I, s_run_mn[wid][id]), f < rc ? f : rc);
+								}
+								if (v) found++; else notfound++;
+								if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + d), (long long)idr);
+							}
 						}
 					}
+					const uint32_t lm = __ballot_sync(0xffffffffu, left);
+					if (left) s_resid[wid][n_res + __popc(lm & lt_mask)] = (uint8_t)q;
+					n_res += __popc(lm);
 				}
-				const uint32_t km = __ballot_sync(0xffffffffu, keep);
 				__syncwarp();
-				if (keep) s_resid[wid][n_keep + __popc(km & lt_mask)] = (uint8_t)q;
-				n_keep += __popc(km);
+				// C4a. the rest through the negative filter; what passes is compacted again (in place: a slot is rewritten
+				// only after the batch that held it was read)
+				if (I.filter) {
+					uint32_t n_keep = 0;
+					#pragma unroll 1
+					for (uint32_t base = 0; base < n_res; base += 32) {
+						const uint32_t i = base + lane;
+						bool keep = false;
+						uint32_t q = 0;
+						if (i < n_res) {
+							q = s_resid[wid][i];
+							const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
+							keep = runid[q] == kTagOverflow || filter_maybe(I, f < rc ? f : rc);
+							if (!keep) {
+								notfound++;
+								if (MODE == kLookupIds) {
+									const uint32_t id = runid[q];
+									__stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + (q - s_run_q[wid][id])), -1ll);
+								}
+							}
+						}
+						const uint32_t km = __ballot_sync(0xffffffffu, keep);
+						__syncwarp();
+						if (keep) s_resid[wid][n_keep + __popc(km & lt_mask)] = (uint8_t)q;
+						n_keep += __popc(km);
+					}
+					n_res = n_keep;
+					__syncwarp();
+				}
 			}
-			n_res = n_keep;
+			// C2 (phase 0: the first k-mer of every run) / C4b (phase 1: what C3 and the filter left): the whole lookup
+			const uint32_t n_items = phase == 0 ? n_anch : n_res;
+			#pragma unroll 1
+			for (uint32_t base = 0; base < n_items; base += 32) {
+				const uint32_t i = base + lane;
+				if (i < n_items) {
+					uint32_t q, id;
+					if (phase == 0) { id = i; q = s_run_q[wid][id]; }
+					else { q = s_resid[wid][i]; id = runid[q]; }
+					uint32_t mn;
+					uint64_t o = 0;
+					if (phase == 1 && id != kTagOverflow) {
+						mn = s_run_mn[wid][id];
+					} else {
+						uint32_t best = 0xFFFFFFFFu;
+						for (uint32_t e = q; e < q + w; e++) best = min(best, keys[kidx(e)]);
+						mn = mini_from_key(best);
+						if (phase == 0) s_run_mn[wid][id] = mn;
+					}
+					if (MODE == kLookupIds) {
+						if (id != kTagOverflow) {
+							o = s_run_o[ow][id] + (q - s_run_q[wid][id]);
+						} else {
+							const uint64_t r = find_read(read_off, n_reads, reads_per_base, t0 + q);
+							o = __ldg(kmer_off + r) + (t0 + q - __ldg(read_off + r));
+						}
+					}
+					const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
+					const uint64_t x = f < rc ? f : rc;
+					uint64_t T = 0;
+					const bool pass = !(phase == 0 && filter_anchors) || filter_maybe(I, x);
+					const int64_t idr = pass ? lookup_one<SMALL>(I, x, mn, &T) : -1;
+					if (idr >= 0) found++; else notfound++;
+					if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + o), (long long)idr);
+					if (phase == 0) {
+						uint32_t flag = 0, dmax = 0;
+						if (idr >= 0) {
+							const bool same = window_at(I.seq, T, k) == f;
+							flag = 1u | (same ? 2u : 0u);
+							const uint4 bd = __ldg(I.bucket + mn);
+							const uint64_t bstart = ((uint64_t)bd.y << 32) | bd.x;
+							// the scan may match past the bucket's end (blight.cpp:732-739 never looks at the length again):
+							// no prediction from there, valid[] is defined per bucket
+							if (T - bstart < bd.z) dmax = (uint32_t)min(same ? bstart + bd.z - 1 - T : T - bstart, (uint64_t)0xFFFF);
+						}
+						s_run_T[wid][id] = T;
+						s_run_flag[wid][id] = (uint8_t)flag;
+						s_run_dmax[wid][id] = (uint16_t)dmax;
+					}
+				}
+			}
 			__syncwarp();
-		}
-		// C4b. the whole lookup, compacted
-		#pragma unroll 1
-		for (uint32_t base = 0; base < n_res; base += 32) {
-			const uint32_t i = base + lane;
-			if (i < n_res) {
-				const uint32_t q = s_resid[wid][i];
-				const uint32_t id = s_runid[wid][q];
-				const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
-				const int64_t idr = lookup_one<SMALL>(I, f < rc ? f : rc, s_run_mn[wid][id]);
-				if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + (q - s_run_q[wid][id])), (long long)idr);
-				if (idr >= 0) found++; else notfound++;
-			}
 		}
 	}
 
@@ -650,7 +733,7 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
                     const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
                     uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
                     cudaStream_t stream) {
-	if (MODE != kEmitPairs && v.valid && use_superkmer_kernel(MODE == kLookupIds, v.pos_id != nullptr)) {
+	if (MODE != kEmitPairs && v.valid && k - m + 1 >= 8 && use_superkmer_kernel(MODE == kLookupIds, v.pos_id != nullptr)) {
 		launch_reads_sk<MODE == kEmitPairs ? kLookupCount : MODE, SMALL>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
 		                                                                strip_lo, strip_hi, al, d_ids, d_ctr, stream);
 		return;
