@@ -89,7 +89,7 @@ enum ReadsMode { kEmitPairs = 0, kLookupIds = 1, kLookupCount = 2 };
 // first read r in [0, n_reads) with off[r+1] > p, i.e. the read containing base position p (or the gap before it).
 // Starts from the position a uniform read length would give and brackets the answer exponentially: 2-3 loads for
 // the usual near-uniform batches, a plain binary search in the worst case.
-__device__ __forceinline__ uint64_t find_read(const uint64_t* __restrict__ off, uint64_t n_reads, double reads_per_base, uint64_t p) {
+__device__ __noinline__ uint64_t find_read(const uint64_t* __restrict__ off, uint64_t n_reads, double reads_per_base, uint64_t p) {
 	uint64_t g = (uint64_t)((double)p * reads_per_base);
 	if (g > n_reads - 1) g = n_reads - 1;
 	uint64_t lo, hi;  // invariant: answer in [lo, hi]
@@ -347,6 +347,21 @@ struct ReadCursor {
 	}
 };
 
+// cold paths, kept out of line so that the strip loop stays dense in the instruction cache
+__device__ __noinline__ uint4 load16_slow(const char* __restrict__ p, uint32_t n) {  // n < 16 valid bytes, or p unaligned
+	unsigned char ch[16];
+	#pragma unroll 1
+	for (uint32_t j = 0; j < 16; j++) ch[j] = j < n ? (unsigned char)p[j] : (unsigned char)'A';
+	return *reinterpret_cast<uint4*>(ch);
+}
+
+__device__ __noinline__ uint32_t window_min_slow(const uint32_t* keys, uint32_t q, uint32_t w) {
+	uint32_t best = 0xFFFFFFFFu;
+	#pragma unroll 1
+	for (uint32_t e = q; e < q + w; e++) best = min(best, keys[kidx(e)]);
+	return best;
+}
+
 template <int MODE, bool SMALL>
 __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                        const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
@@ -390,14 +405,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 			const uint32_t b0 = lane * 16;
 			uint32_t word = 0, badw = 0;
 			if (b0 < n_load) {
+				const uint4 v = (aligned16 && b0 + 16 <= n_load) ? __ldcs(reinterpret_cast<const uint4*>(bases + t0 + b0))
+				                                                  : load16_slow(bases + t0 + b0, n_load - b0);
 				unsigned char ch[16];
-				if (aligned16 && b0 + 16 <= n_load) {
-					const uint4 v = __ldcs(reinterpret_cast<const uint4*>(bases + t0 + b0));
-					*reinterpret_cast<uint4*>(ch) = v;
-				} else {
-					#pragma unroll
-					for (int j = 0; j < 16; j++) ch[j] = (b0 + j < n_load) ? (unsigned char)bases[t0 + b0 + j] : (unsigned char)'A';
-				}
+				*reinterpret_cast<uint4*>(ch) = v;
 				#pragma unroll
 				for (int j = 0; j < 16; j++) {
 					const uint32_t c = nuc_code(ch[j]);
@@ -547,13 +558,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 								left = false;
 								bool v;
 								int64_t idr = -1;
-								if (MODE == kLookupIds && I.pos_id) {
+								if (MODE == kLookupIds) {  // the launcher sends id queries here only when the table exists
 									const uint32_t pid = __ldg(I.pos_id + Tp);
 									v = pid != 0xFFFFFFFFu;
 									if (v) idr = (int64_t)pid;
 								} else {
 									v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
-									if (v && MODE == kLookupIds) idr = id_of_found<SMALL>(I, load_bucket(I, s_run_mn[wid][id]), f < rc ? f : rc);
 								}
 								if (v) found++; else notfound++;
 								if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + d), (long long)idr);
@@ -609,9 +619,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 					if (phase == 1 && id != kTagOverflow) {
 						mn = s_run_mn[wid][id];
 					} else {
-						uint32_t best = 0xFFFFFFFFu;
-						for (uint32_t e = q; e < q + w; e++) best = min(best, keys[kidx(e)]);
-						mn = mini_from_key(best);
+						mn = mini_from_key(window_min_slow(keys, q, w));
 						if (phase == 0) s_run_mn[wid][id] = mn;
 					}
 					if (MODE == kLookupIds) {
@@ -711,8 +719,9 @@ bool use_superkmer_kernel(bool want_ids, bool has_pos_id) {
 		const char* e = getenv("BLIGHT_READS_KERNEL");
 		return !e ? 0 : (e[0] == 'p' ? 1 : (e[0] == 's' ? 2 : 0));
 	}();
+	if (want_ids && !has_pos_id) return false;  // ids without the table: every k-mer needs its MPHF rank anyway (1.25e10 vs 1.31e10 plain)
 	if (forced) return forced == 2;
-	return !want_ids || has_pos_id;
+	return true;
 }
 
 template <int MODE, bool SMALL>

@@ -222,7 +222,7 @@ __device__ __forceinline__ uint32_t rank_in_sector(const uint32_t (&w)[8], uint3
 }
 
 // fallback map (bbhash.h:567-575), sorted by key: rank of x, or false
-__device__ __forceinline__ bool fallback_rank(const DevIndexView& I, const uint4& m1, const uint4& m2, uint64_t x, uint32_t& rank) {
+__device__ __noinline__ bool fallback_rank(const DevIndexView& I, const uint4& m1, const uint4& m2, uint64_t x, uint32_t& rank) {
 	const uint64_t fb_off = ((uint64_t)m1.w << 32) | m1.z;
 	uint32_t lo = 0, hi = m2.x;
 	while (lo < hi) {
