@@ -27,7 +27,16 @@ SYMBOLS = [
     "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
+    "blight_part_dispatch", "blight_part_lookup", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
 ]
+MAX_RANKS = 16
+RUN_RECORD_BYTES = 32
+
+
+class PartRoute(C.Structure):
+    """blight_part_route (include/blight_b200.h)"""
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("lb", C.c_uint32), ("reserved", C.c_uint32),
+                ("cuts", C.c_uint32 * (MAX_RANKS + 1)), ("inbox", C.c_void_p * MAX_RANKS), ("cap", C.c_uint64)]
 
 
 class BlightError(RuntimeError):
@@ -93,6 +102,12 @@ def lib() -> C.CDLL:
     L.blight_owner_scatter.argtypes = [vp, vp, u64, vp, u32, u32, vp, vp, vp, vp, vp]
     L.blight_scatter_ids.argtypes = [vp, vp, u64, vp, vp]
     L.blight_launch_count.restype = u64
+    L.blight_part_dispatch.argtypes = [u32, u32, vp, vp, vp, u64, u64, u64, u64, C.POINTER(PartRoute), vp, vp, vp, vp]
+    L.blight_part_lookup.argtypes = [vp, u32, C.POINTER(vp), vp, C.POINTER(vp), u64, vp, vp]
+    L.blight_peer_alloc.argtypes = [u64, C.POINTER(vp), C.c_char_p]
+    L.blight_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.blight_peer_close.argtypes = [vp]
+    L.blight_peer_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -291,6 +306,64 @@ class DeviceIndex:
         if getattr(self, "_h", None) and self._h.value and _lib is not None:
             _lib.blight_index_free(self._h)
             self._h = C.c_void_p()
+
+
+class PeerBuffer:
+    """Device buffer that the other processes of the box can map (CUDA IPC). `handle` (64 bytes) goes to the peers,
+    which call PeerBuffer.open(handle). Exposes __cuda_array_interface__ so torch can view it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int, handle: bytes, owner: bool):
+        self.ptr, self.nbytes, self.handle, self._owner = ptr, nbytes, handle, owner
+
+    @classmethod
+    def alloc(cls, nbytes: int) -> "PeerBuffer":
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        _check(lib().blight_peer_alloc(nbytes, C.byref(p), h))
+        return cls(p.value, nbytes, h.raw, True)
+
+    @classmethod
+    def open(cls, handle: bytes, nbytes: int) -> "PeerBuffer":
+        p = C.c_void_p()
+        _check(lib().blight_peer_open(handle, C.byref(p)))
+        return cls(p.value, nbytes, handle, False)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def tensor(self, dtype, device):
+        """torch view of the whole buffer (no copy); the PeerBuffer must outlive it."""
+        import torch
+        return torch.as_tensor(self, device=device).view(dtype)
+
+    def close(self):
+        if self.ptr and _lib is not None:
+            (_lib.blight_peer_free if self._owner else _lib.blight_peer_close)(C.c_void_p(self.ptr))
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def part_dispatch(k, m, bases, read_off, kmer_off, route: PartRoute, counts, ctr, err, pos_begin=0, pos_end=None, stream=None):
+    """Source side of the fused partitioned path: super-k-mer records of the k-mers starting in [pos_begin, pos_end)
+    stored into the owners' inboxes. kmer_off None = counting mode."""
+    total = bases.numel()
+    _check(lib().blight_part_dispatch(k, m, _ptr(bases), _ptr(read_off), _ptr(kmer_off), read_off.numel() - 1, total, pos_begin,
+                                      total if pos_end is None else pos_end, C.byref(route), _ptr(counts), _ptr(ctr), _ptr(err),
+                                      _stream_handle(stream)))
+
+
+def part_lookup(index: "DeviceIndex", regions: Sequence[int], counts, out_ptrs: Optional[Sequence[int]], max_records: int, ctr, stream=None):
+    """Owner side: looks the received runs up and stores the ids into the sources' id buffers (out_ptrs None = counting)."""
+    world = len(regions)
+    reg = (C.c_void_p * world)(*regions)
+    outp = (C.c_void_p * world)(*out_ptrs) if out_ptrs is not None else None
+    _check(lib().blight_part_lookup(index._h, world, reg, _ptr(counts), outp, max_records, _ptr(ctr), _stream_handle(stream)))
 
 
 def reads_to_kmers(k: int, m: int, bases, read_off, kmer_off, total_kmers: int, stream=None):

@@ -61,7 +61,7 @@ __device__ __forceinline__ uint32_t pick7(const uint32_t (&w)[8], uint32_t j) {
 // Reference loop form of the 2^b-window scan (blight.cpp:730-739): slide one base at a time. Used for k < 8 or b < 3.
 // canon(window) == x  <=>  window == x or window == rx, because x is canonical (x <= rx).
 // Returns the index of a matching window, or -1.
-__device__ __noinline__ int32_t scan_windows_loop(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
+static __device__ __noinline__ int32_t scan_windows_loop(const uint32_t* __restrict__ seq, uint64_t P, uint32_t k, uint32_t nwin,
                                                   uint64_t x, uint64_t rx) {
 	const uint64_t wi = P >> 4;
 	const uint32_t s = 2u * (uint32_t)(P & 15);
@@ -222,7 +222,7 @@ __device__ __forceinline__ uint32_t rank_in_sector(const uint32_t (&w)[8], uint3
 }
 
 // fallback map (bbhash.h:567-575), sorted by key: rank of x, or false
-__device__ __noinline__ bool fallback_rank(const DevIndexView& I, const uint4& m1, const uint4& m2, uint64_t x, uint32_t& rank) {
+static __device__ __noinline__ bool fallback_rank(const DevIndexView& I, const uint4& m1, const uint4& m2, uint64_t x, uint32_t& rank) {
 	const uint64_t fb_off = ((uint64_t)m1.w << 32) | m1.z;
 	uint32_t lo = 0, hi = m2.x;
 	while (lo < hi) {

@@ -7,6 +7,13 @@ PartitionedSet   large indices: the 2^n MPHF groups are cut into `world` contigu
                  -> bin (canon, minimizer) by owner -> ONE all-to-all out -> lookup at the owner -> ONE all-to-all back
                  -> scatter into read order. Ids are global in both modes.
 
+PartitionedSet has two data paths. `query_reads_fused` is the product on NVLink boxes: the exchange is fused into the
+two kernels either side of it (csrc/part_kernels.cu) — the source stores one 32-byte record per super-k-mer straight into
+the owner's inbox (peer memory), the owner stores ids straight into the source's id buffer; the only collectives are an
+all-to-all of `world` record counts per sub-batch (which is also the barrier) and one all-reduce of the counters per
+batch. `query_reads` is the plain formulation (NCCL all-to-all of (canon, minimizer) out and ids back), kept as the
+fallback when an inbox overflows and as the path the CPU `gloo` tests drive.
+
 The routing (`PartitionPlan`, `exchange_lookup`) is device-agnostic torch code so that world_size-2 `gloo` tests on CPU
 exercise exactly the logic the NCCL path runs; on CUDA the binning and the final scatter are the library's own kernels
 (blight_owner_count / blight_owner_scatter / blight_scatter_ids), never a torch sort.
@@ -194,6 +201,111 @@ class PartitionedSet:
         cuts, lb, k, m = meta[0]
         local = api.FlatIndex.load(os.path.join(workdir, f"part{rank}.blflat"))
         return cls(PartitionPlan(list(cuts), lb), local, device, k, m, group)
+
+    # ---- fused path: peer-memory stores inside the kernels -------------------------------------------------------
+    def enable_fused(self, max_kmers: int = 0, sub_positions: int = 16 << 20, records_per_position: float = 0.25):
+        """Allocates and exchanges the peer buffers: an inbox of 2 (double buffer) x world regions of `cap` records, and
+        (max_kmers > 0) an id buffer of max_kmers int64 that the owners write into. sub_positions = base positions per
+        sub-batch (one dispatch + one lookup kernel each)."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        dev = torch.device("cuda", self.index.device)
+        self._sub = max(256, (int(sub_positions) // 256) * 256)
+        self._cap = max(1024, int(self._sub * records_per_position))
+        self._world, self._rank = world, rank
+        region_bytes = self._cap * api.RUN_RECORD_BYTES
+        self._inbox = api.PeerBuffer.alloc(2 * world * region_bytes)
+        self._ids = api.PeerBuffer.alloc(max(int(max_kmers), 1) * 8) if max_kmers > 0 else None
+        self._ids_cap = int(max_kmers)
+        mine = (self._inbox.handle, self._ids.handle if self._ids else b"", self._ids_cap)
+        everyone = [None] * world
+        if world > 1:
+            dist.all_gather_object(everyone, mine, group=self.group)
+        else:
+            everyone = [mine]
+        self._peers = []  # keep the mappings alive
+        inbox_ptr, ids_ptr = [0] * world, [0] * world
+        for r, (hi, hd, cap_r) in enumerate(everyone):
+            if r == rank:
+                inbox_ptr[r], ids_ptr[r] = self._inbox.ptr, (self._ids.ptr if self._ids else 0)
+                continue
+            pb = api.PeerBuffer.open(hi, 2 * world * region_bytes)
+            self._peers.append(pb)
+            inbox_ptr[r] = pb.ptr
+            if hd:
+                pd = api.PeerBuffer.open(hd, cap_r * 8)
+                self._peers.append(pd)
+                ids_ptr[r] = pd.ptr
+        self._peer_ids = ids_ptr
+        self._routes, self._regions = [], []
+        for b in range(2):
+            rt = api.PartRoute()
+            rt.world, rt.rank, rt.lb, rt.cap = world, rank, self.plan.lb, self._cap
+            for i, c in enumerate(self.plan.cuts):
+                rt.cuts[i] = c
+            for d in range(world):  # my region in owner d's inbox: [buffer b][source = me]
+                rt.inbox[d] = inbox_ptr[d] + (b * world + rank) * region_bytes
+            self._routes.append(rt)
+            self._regions.append([self._inbox.ptr + (b * world + s_) * region_bytes for s_ in range(world)])
+        self._counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
+        self._recv_counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
+        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.barrier(group=self.group)
+
+    def ids_view(self, total_kmers: int) -> torch.Tensor:
+        """The first total_kmers ids of this rank's id buffer (written by the owners; valid after query_reads_fused returns
+        and until the next call)."""
+        dev = torch.device("cuda", self.index.device)
+        return self._ids.tensor(torch.int64, dev)[:total_kmers]
+
+    def query_reads_fused(self, bases: torch.Tensor, read_off: torch.Tensor, kmer_off: Optional[torch.Tensor] = None,
+                          total_kmers: int = 0, want_ids: bool = True, check_overflow: bool = True):
+        """Reads held by THIS rank -> (ids in read order or None, GLOBAL counters [found, not_found, queries, invalid] summed
+        over all ranks). Collective: every rank of the group must call it, with the same want_ids."""
+        if not hasattr(self, "_inbox"):
+            raise RuntimeError("call enable_fused() first")
+        world = self._world
+        dev = bases.device
+        if want_ids and (self._ids is None or total_kmers > self._ids_cap):
+            raise ValueError("enable_fused(max_kmers=...) is smaller than this batch")
+        ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
+        total = bases.numel()
+        n_sub = (total + self._sub - 1) // self._sub
+        if world > 1:
+            t = torch.tensor([n_sub], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            n_sub = int(t.item())
+        self._err.zero_()
+        koff = kmer_off if want_ids else None
+        out_ptrs = self._peer_ids if want_ids else None
+        for i in range(n_sub):
+            b = i & 1
+            cnt, rcv = self._counts[b], self._recv_counts[b]
+            cnt.zero_()
+            if i * self._sub < total:
+                api.part_dispatch(self.k, self.m, bases, read_off, koff, self._routes[b], cnt, ctr, self._err,
+                                  i * self._sub, min(total, (i + 1) * self._sub))
+            if world > 1:
+                dist.all_to_all_single(rcv, cnt, group=self.group)  # the counts, and the barrier that publishes the records
+            else:
+                rcv = cnt
+            api.part_lookup(self.index, self._regions[b], rcv, out_ptrs, world * self._cap, ctr)
+        e = self._err.to(torch.int64)
+        if world > 1:
+            dist.all_reduce(e, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(ctr, group=self.group)  # also the barrier after which every id has landed
+        if check_overflow:
+            host = torch.cat([e, ctr]).cpu()
+            if int(host[1 + api.CTR_INVALID]):
+                raise api.InvalidBase(api.ERR_INVALID_BASE, "Invalid char in DNA")  # std::domain_error, kmer.h:68
+            if int(host[0]):
+                # a region overflowed (far more super-k-mers per base than a read batch has): the plain paths have no such limit
+                if world == 1:
+                    return self.index.query_reads(bases, read_off, kmer_off, total_kmers, want_ids=want_ids)
+                ids, c = self.query_reads(bases, read_off, kmer_off, total_kmers)
+                return (ids if want_ids else None), all_reduce_counters(c, self.group)
+        return (self.ids_view(total_kmers) if want_ids else None), ctr
 
     def query_kmers(self, canon: torch.Tensor, mini: torch.Tensor) -> torch.Tensor:
         return exchange_lookup(canon, mini, self.plan, lambda c, mn: self.index.query_kmers(c, mini=mn), self.group)

@@ -151,6 +151,42 @@ int blight_owner_scatter(const uint64_t* d_canon, const uint32_t* d_mini, uint64
 /* d_out[d_src[i]] = d_ids_back[i]: ids returned by the owners back into query order. */
 int blight_scatter_ids(const int64_t* d_ids_back, const uint64_t* d_src, uint64_t n, int64_t* d_out, void* stream);
 
+/* ---- the same mode with the exchange fused into the kernels (peer-memory stores over NVLink; no reference
+ * counterpart). The source GPU cuts its reads into super-k-mers (runs of equal minimizer, kmer.h:629-693) and stores
+ * one 32-byte record per run straight into the owner's inbox; the owner looks the run up and stores the identifiers
+ * straight into the source's id buffer. Between the two kernels the caller exchanges the per-pair record counts
+ * (one tiny all-to-all, which is also the barrier). ------------------------------------------------------------- */
+
+#define BLIGHT_MAX_RANKS 16
+#define BLIGHT_RUN_RECORD_BYTES 32
+
+typedef struct blight_part_route {
+	uint32_t world, rank;                /* ranks of the partition, this (source) rank */
+	uint32_t lb;                         /* log2(buckets per MPHF group): group = minimizer >> lb (blight.cpp:722) */
+	uint32_t reserved;
+	uint32_t cuts[BLIGHT_MAX_RANKS + 1]; /* rank r owns MPHF groups [cuts[r], cuts[r+1]) */
+	void* inbox[BLIGHT_MAX_RANKS];       /* DEVICE pointers: this source's region in every owner's inbox (peer memory) */
+	uint64_t cap;                        /* records per region */
+} blight_part_route;
+
+/* Front end + dispatch of the k-mers starting in [pos_begin, pos_end) of a read batch (bounds: multiples of 256, or
+ * the end). d_kmer_off == NULL: counting mode (records carry no output slot). d_counts[world] (records stored per
+ * owner) is ACCUMULATED into; d_ctr gets BLIGHT_CTR_QUERIES / BLIGHT_CTR_INVALID; *d_err |= 1 if a region overflowed
+ * (records beyond `cap` are dropped: the caller must retry with smaller sub-batches). */
+int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
+                         uint64_t n_reads, uint64_t total_bases, uint64_t pos_begin, uint64_t pos_end, const blight_part_route* route,
+                         uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream);
+/* Owner side: regions[s] = records received from source s (device pointer), d_counts[s] = how many (DEVICE array, so
+ * no host round trip), out[s] = id buffer of source s (peer pointer; out == NULL: counting mode). max_records bounds
+ * the total for the grid size. d_ctr gets BLIGHT_CTR_FOUND / BLIGHT_CTR_NOT_FOUND (accumulated). */
+int blight_part_lookup(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts,
+                       int64_t* const* out, uint64_t max_records, uint64_t* d_ctr, void* stream);
+/* Device buffers other processes of the box can map (CUDA IPC): alloc + 64-byte handle here, open there. */
+int blight_peer_alloc(uint64_t bytes, void** d_ptr, unsigned char* handle64);
+int blight_peer_open(const unsigned char* handle64, void** d_ptr);
+int blight_peer_close(void* d_ptr);
+int blight_peer_free(void* d_ptr);
+
 /* Number of kernel launches issued by this library in the calling process (all threads) since load. */
 uint64_t blight_launch_count(void);
 

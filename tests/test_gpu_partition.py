@@ -1,0 +1,135 @@
+"""The fused bucket-partitioned path (csrc/part_kernels.cu: super-k-mer records dispatched to the owner's inbox, ids
+stored back into the source's buffer) against the oracle, on ONE GPU: a loop-back partition of one rank, and a simulated
+partition of three ranks whose inboxes and id buffers all live on GPU 0 (the peer pointers are then local pointers, the
+kernels are exactly the ones the NVLink path runs)."""
+import numpy as np
+import pytest
+
+from blight_b200 import api, synth
+from blight_b200 import dist as bdist
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _dev_batch(torch, rb, ro, k=31):
+    koff = synth.kmer_offsets(ro, k)
+    return (torch.from_numpy(rb).cuda(), torch.from_numpy(ro.astype(np.int64)).cuda(),
+            torch.from_numpy(koff.astype(np.int64)).cuda(), int(koff[-1]))
+
+
+@pytest.mark.parametrize("shape", [(9, 6, 6), (7, 5, 0), (11, 8, 8)])
+def test_loopback_partition_matches_oracle(shape, tmp_path, torch_cuda):
+    torch = torch_cuda
+    m, n, b = shape
+    g, ub, uo, rb, ro = common.synthetic(600_000, 6000, seed=11 + m, sub_rate=0.03)
+    flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=m, n=n, s=0, b=b, threads=0)
+    port = common.cport_of(flat, tmp_path)
+    want, wctr = port.query_reads(rb, ro)
+    info = flat.info()
+    plan = bdist.PartitionPlan([0, info["n_mphf"]], 2 * m - 1 - n)
+    ps = bdist.PartitionedSet(plan, flat, 0, 31, m)
+    d_b, d_o, d_k, total = _dev_batch(torch, rb, ro)
+    ps.enable_fused(max_kmers=total, sub_positions=1 << 17)  # several sub-batches, both inbox buffers
+    n0 = api.launch_count()
+    ids, ctr = ps.query_reads_fused(d_b, d_o, d_k, total)
+    torch.cuda.synchronize()
+    assert api.launch_count() >= n0 + 2
+    assert np.array_equal(ids.cpu().numpy(), want)
+    assert [int(c) for c in ctr.cpu()[:3]] == [int(wctr[0]), int(wctr[1]), int(wctr[2])]
+    _, ctr2 = ps.query_reads_fused(d_b, d_o, want_ids=False)
+    torch.cuda.synchronize()
+    assert torch.equal(ctr2.cpu(), ctr.cpu())
+
+
+def test_loopback_ragged_and_tiny_reads(tmp_path, torch_cuda):
+    """Read lengths 1..4000 and a block of reads of 31-36 bases (more than 64 super-k-mers per 256-base strip: the run
+    table overflows and the surplus k-mers travel as single-k-mer records); invalid bases raise like the reference."""
+    torch = torch_cuda
+    rng = np.random.default_rng(3)
+    g, ub, uo, _, _ = common.synthetic(400_000, 10, seed=19)
+    flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=9, n=6, s=0, b=5, threads=0)
+    port = common.cport_of(flat, tmp_path)
+    lens = np.concatenate([rng.integers(1, 80, 400), rng.integers(31, 37, 3000), rng.integers(100, 4000, 200), [31, 30, 32, 2048, 4096 + 30]])
+    rng.shuffle(lens)
+    starts = rng.integers(0, len(g) - 4200, len(lens))
+    rb = np.concatenate([g[s:s + l] for s, l in zip(starts, lens)])
+    ro = np.zeros(len(lens) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=ro[1:])
+    want, wctr = port.query_reads(rb, ro)
+    plan = bdist.PartitionPlan([0, flat.info()["n_mphf"]], 2 * 9 - 1 - 6)
+    ps = bdist.PartitionedSet(plan, flat, 0, 31, 9)
+    d_b, d_o, d_k, total = _dev_batch(torch, rb, ro)
+    ps.enable_fused(max_kmers=total, sub_positions=1 << 16, records_per_position=1.0)
+    ids, ctr = ps.query_reads_fused(d_b, d_o, d_k, total)
+    torch.cuda.synchronize()
+    assert np.array_equal(ids.cpu().numpy(), want)
+    assert (int(ctr[0]), int(ctr[1])) == (int(wctr[0]), int(wctr[1]))
+    # an inbox too small for the batch: detected, answered through the plain path, same ids
+    ps2 = bdist.PartitionedSet(plan, flat, 0, 31, 9)
+    ps2.enable_fused(max_kmers=total, sub_positions=1 << 16, records_per_position=0.001)
+    ids2, ctr3 = ps2.query_reads_fused(d_b, d_o, d_k, total)
+    torch.cuda.synchronize()
+    assert np.array_equal(ids2.cpu().numpy()[:total], want)
+    bad = rb.copy()
+    bad[int(ro[5]) + 3] = ord("N")
+    lens5 = int(ro[6] - ro[5])
+    d_bad = torch.from_numpy(bad).cuda()
+    if lens5 >= 31:
+        with pytest.raises(api.InvalidBase):
+            ps.query_reads_fused(d_bad, d_o, d_k, total)
+
+
+def test_three_owners_two_sources_on_one_gpu(tmp_path, torch_cuda):
+    """Partition over 3 ranks simulated on GPU 0: ranks 0 and 1 hold reads, every rank owns a slice of the index."""
+    torch = torch_cuda
+    m, n, b, world = 9, 8, 6, 3
+    g, ub, uo, rb, ro = common.synthetic(800_000, 8000, seed=23, sub_rate=0.02)
+    flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=m, n=n, s=0, b=b, threads=0)
+    port = common.cport_of(flat, tmp_path)
+    want, wctr = port.query_reads(rb, ro)
+    plan = bdist.PartitionPlan.balanced(flat.group_sizes(), world, 2 * m - 1 - n)
+    owners = [flat.slice(*plan.group_range(r)).upload(0) for r in range(world)]
+    # two sources: first and second half of the reads
+    half = (len(ro) - 1) // 2
+    parts = []
+    for lo, hi in ((0, half), (half, len(ro) - 1)):
+        o = ro[lo:hi + 1] - ro[lo]
+        parts.append((rb[int(ro[lo]):int(ro[hi])], o, want[int(synth.kmer_offsets(ro, 31)[lo]):int(synth.kmer_offsets(ro, 31)[hi])]))
+    cap = 1 << 16
+    inbox = torch.zeros(world * world * cap * api.RUN_RECORD_BYTES, dtype=torch.uint8, device="cuda")  # [owner][source][cap]
+    counts = torch.zeros(world, world, dtype=torch.int64, device="cuda")                              # [source][owner]
+    ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ids_bufs, totals = [], []
+    for s, (pb, po, _) in enumerate(parts):
+        d_b, d_o, d_k, total = _dev_batch(torch, pb, po)
+        ids_bufs.append(torch.full((total,), -7, dtype=torch.int64, device="cuda"))
+        totals.append(total)
+        rt = api.PartRoute()
+        rt.world, rt.rank, rt.lb, rt.cap = world, s, plan.lb, cap
+        for i, c in enumerate(plan.cuts):
+            rt.cuts[i] = c
+        for d in range(world):
+            rt.inbox[d] = inbox.data_ptr() + (d * world + s) * cap * api.RUN_RECORD_BYTES
+        api.part_dispatch(31, m, d_b, d_o, d_k, rt, counts[s], ctr, err)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    out_ptrs = [ids_bufs[0].data_ptr(), ids_bufs[1].data_ptr(), 0]
+    for d in range(world):
+        regions = [inbox.data_ptr() + (d * world + s) * cap * api.RUN_RECORD_BYTES for s in range(world)]
+        cnt_d = counts[:, d].contiguous()
+        assert int(cnt_d[2]) == 0 and int(cnt_d[0]) > 0
+        api.part_lookup(owners[d], regions, cnt_d, out_ptrs, world * cap, ctr)
+    torch.cuda.synchronize()
+    for s in range(2):
+        assert np.array_equal(ids_bufs[s].cpu().numpy(), parts[s][2]), s
+    assert (int(ctr[0]), int(ctr[1]), int(ctr[2])) == (int(wctr[0]), int(wctr[1]), int(wctr[2]))
