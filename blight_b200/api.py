@@ -27,7 +27,7 @@ SYMBOLS = [
     "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
-    "blight_part_dispatch", "blight_part_lookup", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
+    "blight_part_dispatch", "blight_part_lookup", "blight_part_scatter", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
 ]
 MAX_RANKS = 16
 RUN_RECORD_BYTES = 32
@@ -36,7 +36,8 @@ RUN_RECORD_BYTES = 32
 class PartRoute(C.Structure):
     """blight_part_route (include/blight_b200.h)"""
     _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("lb", C.c_uint32), ("reserved", C.c_uint32),
-                ("cuts", C.c_uint32 * (MAX_RANKS + 1)), ("inbox", C.c_void_p * MAX_RANKS), ("cap", C.c_uint64)]
+                ("cuts", C.c_uint32 * (MAX_RANKS + 1)), ("inbox", C.c_void_p * MAX_RANKS), ("cap", C.c_uint64),
+                ("kcap", C.c_uint64), ("side", C.c_void_p)]
 
 
 class BlightError(RuntimeError):
@@ -104,6 +105,7 @@ def lib() -> C.CDLL:
     L.blight_launch_count.restype = u64
     L.blight_part_dispatch.argtypes = [u32, u32, vp, vp, vp, u64, u64, u64, u64, C.POINTER(PartRoute), vp, vp, vp, vp]
     L.blight_part_lookup.argtypes = [vp, u32, C.POINTER(vp), vp, C.POINTER(vp), u64, vp, vp]
+    L.blight_part_scatter.argtypes = [vp, u64, vp, vp, u64, u32, u64, vp, vp]
     L.blight_peer_alloc.argtypes = [u64, C.POINTER(vp), C.c_char_p]
     L.blight_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.blight_peer_close.argtypes = [vp]
@@ -358,12 +360,18 @@ def part_dispatch(k, m, bases, read_off, kmer_off, route: PartRoute, counts, ctr
                                       _stream_handle(stream)))
 
 
-def part_lookup(index: "DeviceIndex", regions: Sequence[int], counts, out_ptrs: Optional[Sequence[int]], max_records: int, ctr, stream=None):
-    """Owner side: looks the received runs up and stores the ids into the sources' id buffers (out_ptrs None = counting)."""
+def part_lookup(index: "DeviceIndex", regions: Sequence[int], counts, ret_ptrs: Optional[Sequence[int]], max_records: int, ctr, stream=None):
+    """Owner side: looks the received runs up and stores 32-bit ids into its return region at every source
+    (ret_ptrs None = counting mode)."""
     world = len(regions)
     reg = (C.c_void_p * world)(*regions)
-    outp = (C.c_void_p * world)(*out_ptrs) if out_ptrs is not None else None
-    _check(lib().blight_part_lookup(index._h, world, reg, _ptr(counts), outp, max_records, _ptr(ctr), _stream_handle(stream)))
+    retp = (C.c_void_p * world)(*ret_ptrs) if ret_ptrs is not None else None
+    _check(lib().blight_part_lookup(index._h, world, reg, _ptr(counts), retp, max_records, _ptr(ctr), _stream_handle(stream)))
+
+
+def part_scatter(side_ptr: int, cap: int, counts, ret_ptr: int, kcap: int, world: int, max_records: int, ids, stream=None):
+    """Source side, after the owners answered: return regions -> int64 ids in read order."""
+    _check(lib().blight_part_scatter(side_ptr, cap, _ptr(counts), ret_ptr, kcap, world, max_records, _ptr(ids), _stream_handle(stream)))
 
 
 def reads_to_kmers(k: int, m: int, bases, read_off, kmer_off, total_kmers: int, stream=None):

@@ -1,23 +1,27 @@
 // part_kernels.cu — the bucket-partitioned multi-GPU query path (BASELINE configs[4]), fused with its
 // exchange: super-k-mers travel to the GPU that owns their minimizer bucket and identifiers travel back as plain
-// peer-memory stores over NVLink, inside the two kernels that produce them. No staging buffers, no separate
-// all-to-all of payloads, no scatter pass.
+// peer-memory stores over NVLink, issued by the kernels that produce them. No NCCL payload collectives, no staging in HBM.
 //
 //   k_dispatch_runs   (on the GPU holding the reads)  front end of k_reads_sk (front.cuh: pack, minimizer keys, runs
 //                     of equal minimizer = super-k-mers, kmer.h:629-693) -> one 32-byte record per run {2-bit bases of
-//                     the run, output slot, minimizer, length, source rank} STORED DIRECTLY into the owner's inbox
-//                     (owner = rank whose MPHF-group range holds minimizer >> lb, the reference's MPHF selection,
-//                     blight.cpp:722). Slots of a (source, owner) pair are reserved with a local atomic; only the
-//                     record itself crosses NVLink (~2.7 B per k-mer instead of 12 B of (canon, minimizer)).
-//   k_runs_lookup     (on the owner)  per warp 32 records: the first k-mer of every run through the whole lookup
-//                     (lookup.cuh), every other k-mer of the run against the ONE window next to where the first one
-//                     matched (answer = pos_id / valid of that window, device_index.hpp), the rest through the
-//                     negative filter and the whole lookup; identifiers are STORED DIRECTLY into the source GPU's
-//                     id buffer at the run's output slot. In counting mode nothing travels back but two counters.
+//                     the run, k-mer offset in the (source, owner) stream, minimizer, length, source rank} STORED
+//                     DIRECTLY into the owner's inbox (owner = rank whose MPHF-group range holds minimizer >> lb, the
+//                     reference's MPHF selection, blight.cpp:722). Record slot and k-mer offset of a (source, owner) pair
+//                     are reserved together with ONE local 64-bit atomic, so k-mer offsets are consecutive in slot order.
+//                     Only the record crosses NVLink (~2.7 B per k-mer instead of 12 B of (canon, minimizer)); where
+//                     the run's ids must finally go stays at the source, in a side table.
+//   k_runs_lookup     (on the owner)  per warp 32 consecutive records of one source: the first k-mer of every run
+//                     through the whole lookup (lookup.cuh), every other k-mer of the run against the ONE window next
+//                     to where the first one matched (answer = pos_id / valid of that window, device_index.hpp), the
+//                     rest through the negative filter and the whole lookup. The warp's ids (32-bit) are collected in
+//                     shared memory and STORED DIRECTLY into the source GPU's return region as one contiguous,
+//                     sector-aligned stream (first version: 8-byte stores scattered into the source's id buffer reached
+//                     only 73 GB/s of NVLink). In counting mode nothing travels back but two counters.
+//   k_scatter_runs    (back on the source)  return streams -> int64 ids in read order, through the side table.
 //
-// Ordering between GPUs is the caller's (blight_b200/dist.py): one tiny NCCL all-to-all of the per-pair record counts
-// between the two kernels (it is also the barrier that makes the records visible), one all-reduce of the counters at
-// the end of a batch (the barrier after which every id has landed).
+// Ordering between GPUs is the caller's (blight_b200/dist.py): one tiny NCCL all-to-all of the per-pair counters
+// between dispatch and lookup (it is also the barrier that publishes the records; the one of the NEXT sub-batch
+// publishes the returned ids), one all-reduce of the counters at the end of a batch.
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -32,14 +36,20 @@ namespace {
 
 constexpr int kMaxRanks = BLIGHT_MAX_RANKS;
 constexpr int kRecWords = 5;                  // 4 words of bases + one zero word for the funnel
-constexpr uint32_t kMaxRecKmers = 33;         // k-mers per record: bounds the residual list of a warp
+constexpr uint32_t kMaxRecKmers = 25;         // k-mers per record (k - m + 1 of the usual shapes): bounds a warp's staging
 constexpr int kMaxPairs = 32 * (kMaxRecKmers - 1);
+constexpr int kMaxIds = 32 * kMaxRecKmers;
+constexpr int kResCap = 128;                  // entries of a warp's work list (drained whenever fewer than 32 slots are left)
+constexpr unsigned long long kKmerBits = 40;  // packed pair counter: slots << 40 | k-mers
+constexpr unsigned long long kKmerMask = (1ull << kKmerBits) - 1;
+constexpr uint32_t kIdAbsent = 0xFFFFFFFFu;
 
 struct alignas(32) RunRec {
 	uint32_t bases[4];  // n + k - 1 bases, 2 bits each, first base in the high bits of bases[0]
-	uint64_t o;         // output slot of the run's first k-mer in the source's id buffer
+	uint32_t ko;        // k-mer offset of the run's first k-mer in the (source, owner) stream of this sub-batch
 	uint32_t mn;        // minimizer (bucket) of every k-mer of the run
 	uint32_t n_src;     // bits 0-7: k-mers in the run, bits 8-15: source rank
+	uint32_t spare;
 };
 static_assert(sizeof(RunRec) == 32, "one record = one sector");
 
@@ -48,6 +58,8 @@ struct Route {
 	uint32_t cuts[kMaxRanks + 1];
 	RunRec* inbox[kMaxRanks];  // this source's region in every owner's inbox (peer pointers)
 	uint64_t cap;              // records per region
+	uint64_t kcap;             // k-mers per return region
+	uint4* side;               // local: {o_lo, o_hi, ko, n} of record `slot` bound for owner d at [d * cap + slot]; null = counting
 };
 
 __device__ __forceinline__ uint32_t owner_of(const Route& R, uint32_t mini) {
@@ -148,20 +160,41 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 			#pragma unroll 1
 			for (uint32_t off = 0; __any_sync(0xffffffffu, off < n); off += nmax) {
 				const bool act = off < n;
-				const uint32_t peers = __match_any_sync(0xffffffffu, act ? dst : 0xFFFFu);
+				const uint32_t nn = act ? min(n - off, nmax) : 0u;
+				// lanes bound for the same owner: exclusive prefix and total of their k-mer counts, one warp scan per owner present
+				uint32_t peers = 0, kpre = 0, ktot = 0;
+				uint32_t todo = __ballot_sync(0xffffffffu, act);
+				#pragma unroll 1
+				while (todo) {
+					const uint32_t d0 = __shfl_sync(0xffffffffu, dst, __ffs(todo) - 1);
+					const bool mine = act && dst == d0;
+					uint32_t inc = mine ? nn : 0u;
+					#pragma unroll
+					for (int sh = 1; sh < 32; sh <<= 1) {
+						const uint32_t t = __shfl_up_sync(0xffffffffu, inc, sh);
+						if (lane >= (uint32_t)sh) inc += t;
+					}
+					const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+					const uint32_t grp = __ballot_sync(0xffffffffu, mine);
+					if (mine) { peers = grp; kpre = inc - nn; ktot = tot; }
+					todo &= ~grp;
+				}
 				if (act) {
 					const uint32_t leader = __ffs(peers) - 1;
-					unsigned long long slot0 = 0;
-					if (lane == leader) slot0 = atomicAdd(&counts[dst], (unsigned long long)__popc(peers));
-					slot0 = __shfl_sync(peers, slot0, leader);
-					const uint64_t slot = slot0 + __popc(peers & lt_mask);
-					if (slot < R.cap) {
-						const uint32_t nn = min(n - off, nmax);
+					unsigned long long r0 = 0;
+					if (lane == leader) r0 = atomicAdd(&counts[dst], ((unsigned long long)__popc(peers) << kKmerBits) | ktot);
+					r0 = __shfl_sync(peers, r0, leader);
+					const uint64_t slot = (r0 >> kKmerBits) + __popc(peers & lt_mask);
+					const uint64_t ko = (r0 & kKmerMask) + kpre;
+					if (slot < R.cap && ko + nn <= R.kcap) {
 						const uint4 b = strip_bases64(S.pack, q + off);
 						uint4* dstp = reinterpret_cast<uint4*>(R.inbox[dst] + slot);
-						const uint64_t oo = o + off;
 						dstp[0] = b;
-						dstp[1] = make_uint4((uint32_t)oo, (uint32_t)(oo >> 32), mn, nn | (R.rank << 8));
+						dstp[1] = make_uint4((uint32_t)ko, mn, nn | (R.rank << 8), 0u);
+						if (WANT_O) {
+							const uint64_t oo = o + off;
+							R.side[(uint64_t)dst * R.cap + slot] = make_uint4((uint32_t)oo, (uint32_t)(oo >> 32), (uint32_t)ko, nn);
+						}
 					} else {
 						atomicOr(err, 1u);
 					}
@@ -183,9 +216,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 struct OwnerArgs {
 	uint32_t world, pad;
 	const RunRec* region[kMaxRanks];  // records received from every source
-	int64_t* out[kMaxRanks];          // id buffer of every source (peer pointers), unused in counting mode
+	uint32_t* ret[kMaxRanks];         // this owner's return region at every source (peer pointers), unused in counting mode
 };
-
 
 // k-mer at offset d of a record's bases
 __device__ __forceinline__ uint64_t rec_kmer(const uint32_t* W, uint32_t d, uint32_t k) {
@@ -194,156 +226,129 @@ __device__ __forceinline__ uint64_t rec_kmer(const uint32_t* W, uint32_t d, uint
 	return (((uint64_t)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s)) >> (64 - 2 * k);
 }
 
+// run holding flattened index i, given the inclusive prefix of the runs' sizes (32 entries)
+__device__ __forceinline__ uint32_t run_of(const uint16_t* incl, uint32_t i) {
+	uint32_t lo = 0, hi = 31;
+	#pragma unroll
+	for (int s = 0; s < 5; s++) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (incl[mid] > i) hi = mid; else lo = mid + 1;
+	}
+	return lo;
+}
+
 template <bool WANT_IDS, bool SMALL>
 __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, OwnerArgs A, const unsigned long long* __restrict__ counts,
                                                            uint64_t* __restrict__ ctr) {
-	__shared__ unsigned long long s_pref[kMaxRanks + 1];
+	__shared__ unsigned long long s_pref[kMaxRanks + 1];  // chunks (32 records of one source) before source s
+	__shared__ unsigned long long s_cnt[kMaxRanks];
 	__shared__ uint32_t s_w[kWarps][32][kRecWords + 1];  // +1: odd stride
 	__shared__ uint64_t s_T[kWarps][32];
-	__shared__ uint64_t s_o[WANT_IDS ? kWarps : 1][32];
 	__shared__ uint32_t s_mn[kWarps][32];
 	__shared__ uint16_t s_dmax[kWarps][32];
-	__shared__ uint16_t s_incl[kWarps][32];  // inclusive prefix of (n - 1): k-mers after the first, flattened over the 32 runs
-	__shared__ uint8_t s_n[kWarps][32], s_flag[kWarps][32], s_src[kWarps][32];
-	__shared__ uint16_t s_res[kWarps][kMaxPairs];  // (run << 8) | d of the k-mers left for the whole lookup
+	__shared__ uint16_t s_incl[kWarps][32];  // inclusive prefix of n: the ids of the warp's runs, flattened, live at [incl[r-1], incl[r])
+	__shared__ uint8_t s_flag[kWarps][32];
+	__shared__ uint16_t s_res[kWarps][kResCap];                 // work list: flattened indices waiting for the whole lookup
+	__shared__ uint32_t s_ids[WANT_IDS ? kWarps : 1][kMaxIds];  // the warp's answers, in the order they travel back
 
 	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint32_t ow = WANT_IDS ? wid : 0;
+	const uint32_t iw = WANT_IDS ? wid : 0;
 	const uint32_t k = I.k;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	const bool filter_anchors = I.filter && (I.flags & kFlagFilterAnchors);
+	const bool filter_anchors = (I.flags & kFlagFilterAnchors) != 0;
 	if (threadIdx.x == 0) {
 		unsigned long long acc = 0;
-		for (uint32_t s = 0; s < A.world; s++) { s_pref[s] = acc; acc += counts[s]; }
+		for (uint32_t s = 0; s < A.world; s++) {
+			const unsigned long long c = counts[s] >> kKmerBits;
+			s_cnt[s] = c;
+			s_pref[s] = acc;
+			acc += (c + 31) / 32;
+		}
 		s_pref[A.world] = acc;
 	}
 	__syncthreads();
-	const uint64_t total = s_pref[A.world];
-	const uint64_t n_chunks = (total + 31) / 32;
+	const uint64_t n_chunks = s_pref[A.world];
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
 	uint32_t found = 0, notfound = 0;
 
 	for (uint64_t chunk = (uint64_t)blockIdx.x * kWarps + wid; chunk < n_chunks; chunk += warp_stride) {
-		const uint64_t g = chunk * 32 + lane;
+		uint32_t src = 0;
+		while (src + 1 < A.world && chunk >= s_pref[src + 1]) src++;
+		const uint64_t rec0 = (chunk - s_pref[src]) * 32;
+		const uint32_t n_first = (uint32_t)min((unsigned long long)32, s_cnt[src] - rec0);
 		__syncwarp();
 		// the warp's 32 records into shared memory
-		uint32_t n = 0;
-		if (g < total) {
-			uint32_t s = 0;
-			while (s + 1 < A.world && g >= s_pref[s + 1]) s++;
-			const uint4* rp = reinterpret_cast<const uint4*>(A.region[s] + (g - s_pref[s]));
+		uint32_t n = 0, ko = 0;
+		if (lane < n_first) {
+			const uint4* rp = reinterpret_cast<const uint4*>(A.region[src] + rec0 + lane);
 			const uint4 b = __ldcs(rp), h = __ldcs(rp + 1);
 			uint32_t* W = s_w[wid][lane];
 			W[0] = b.x; W[1] = b.y; W[2] = b.z; W[3] = b.w; W[4] = 0;
-			if (WANT_IDS) s_o[ow][lane] = ((uint64_t)h.y << 32) | h.x;
-			s_mn[wid][lane] = h.z;
-			n = h.w & 0xFFu;
-			s_src[wid][lane] = (uint8_t)((h.w >> 8) & 0xFFu);
+			ko = h.x;
+			s_mn[wid][lane] = h.y;
+			n = min(h.z & 0xFFu, kMaxRecKmers);
 		}
-		s_n[wid][lane] = (uint8_t)n;
-		uint32_t incl = n ? n - 1 : 0;
+		uint32_t incl = n;
 		#pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
 			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
 			if (lane >= (uint32_t)o) incl += t;
 		}
 		s_incl[wid][lane] = (uint16_t)incl;
-		const uint32_t n_pairs = __shfl_sync(0xffffffffu, incl, 31);
-		const uint32_t n_first = (uint32_t)min((uint64_t)32, total - chunk * 32);
+		const uint32_t n_ids = __shfl_sync(0xffffffffu, incl, 31);
+		const uint32_t ko0 = __shfl_sync(0xffffffffu, ko, 0);  // k-mer offsets are consecutive in slot order
 		__syncwarp();
 
-		uint32_t n_res = 0;
+		// Work list of flattened k-mer indices waiting for the whole lookup: first the first k-mer of every run (d == 0), then,
+		// turn by turn, what the one-window prediction left. ONE copy of filter + lookup drains it (instruction cache).
+		uint32_t n_res = n_first, base = 0;
+		if (lane < n_first) s_res[wid][lane] = (uint16_t)(incl - n);
+		bool anchors = true;
+		__syncwarp();
 		#pragma unroll 1
-		for (int phase = 0; phase < 2; phase++) {
-			if (phase == 1) {
-				// every other k-mer of a run: the one window next to where the first one matched
+		do {
+			// drain: negative filter (anchors only if asked to), then the lookup, compacted in place
+			if (I.filter && (!anchors || filter_anchors)) {
+				uint32_t n_keep = 0;
 				#pragma unroll 1
-				for (uint32_t base = 0; base < n_pairs; base += 32) {
-					const uint32_t i = base + lane;
-					bool left = false;
-					uint32_t run = 0, d = 0;
-					if (i < n_pairs) {
-						// first run whose inclusive prefix exceeds i
-						uint32_t lo = 0, hi = 31;
-						#pragma unroll
-						for (int s = 0; s < 5; s++) {
-							const uint32_t mid = (lo + hi) >> 1;
-							if (s_incl[wid][mid] > i) hi = mid; else lo = mid + 1;
-						}
-						run = lo;
-						d = i - (run ? s_incl[wid][run - 1] : 0u) + 1;
-						left = true;
-						const uint32_t flag = s_flag[wid][run];
-						if ((flag & 1) && d <= s_dmax[wid][run]) {
-							const bool same = flag & 2;
-							const uint64_t Ta = s_T[wid][run];
-							const uint64_t Tp = same ? Ta + d : Ta - d;
-							const uint64_t f = rec_kmer(s_w[wid][run], d, k), rc = rc64(f, k);
-							if (window_at(I.seq, Tp, k) == (same ? f : rc)) {
-								left = false;
-								bool v;
-								int64_t idr = -1;
-								if (WANT_IDS) {
-									const uint32_t pid = __ldg(I.pos_id + Tp);
-									v = pid != 0xFFFFFFFFu;
-									if (v) idr = (int64_t)pid;
-								} else {
-									v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
-								}
-								if (v) found++; else notfound++;
-								if (WANT_IDS) A.out[s_src[wid][run]][s_o[ow][run] + d] = idr;
-							}
+				for (uint32_t b0 = 0; b0 < n_res; b0 += 32) {
+					const uint32_t j = b0 + lane;
+					bool keep = false;
+					uint32_t i = 0;
+					if (j < n_res) {
+						i = s_res[wid][j];
+						const uint32_t run = run_of(s_incl[wid], i);
+						const uint32_t d = i - (run ? s_incl[wid][run - 1] : 0u);
+						const uint64_t f = rec_kmer(s_w[wid][run], d, k), rc = rc64(f, k);
+						keep = filter_maybe(I, f < rc ? f : rc);
+						if (!keep) {
+							notfound++;
+							if (WANT_IDS) s_ids[iw][i] = kIdAbsent;
+							if (d == 0) s_flag[wid][run] = 0;
 						}
 					}
-					const uint32_t lm = __ballot_sync(0xffffffffu, left);
-					if (left) s_res[wid][n_res + __popc(lm & lt_mask)] = (uint16_t)((run << 8) | d);
-					n_res += __popc(lm);
-				}
-				__syncwarp();
-				if (I.filter) {
-					uint32_t n_keep = 0;
-					#pragma unroll 1
-					for (uint32_t base = 0; base < n_res; base += 32) {
-						const uint32_t i = base + lane;
-						bool keep = false;
-						uint32_t it = 0;
-						if (i < n_res) {
-							it = s_res[wid][i];
-							const uint32_t run = it >> 8, d = it & 0xFFu;
-							const uint64_t f = rec_kmer(s_w[wid][run], d, k), rc = rc64(f, k);
-							keep = filter_maybe(I, f < rc ? f : rc);
-							if (!keep) {
-								notfound++;
-								if (WANT_IDS) A.out[s_src[wid][run]][s_o[ow][run] + d] = -1ll;
-							}
-						}
-						const uint32_t km = __ballot_sync(0xffffffffu, keep);
-						__syncwarp();
-						if (keep) s_res[wid][n_keep + __popc(km & lt_mask)] = (uint16_t)it;
-						n_keep += __popc(km);
-					}
-					n_res = n_keep;
+					const uint32_t km = __ballot_sync(0xffffffffu, keep);
 					__syncwarp();
+					if (keep) s_res[wid][n_keep + __popc(km & lt_mask)] = (uint16_t)i;
+					n_keep += __popc(km);
 				}
+				n_res = n_keep;
+				__syncwarp();
 			}
-			// phase 0: the first k-mer of every run; phase 1: what the prediction and the filter left. One copy of the lookup.
-			const uint32_t n_items = phase == 0 ? n_first : n_res;
 			#pragma unroll 1
-			for (uint32_t base = 0; base < n_items; base += 32) {
-				const uint32_t i = base + lane;
-				if (i < n_items) {
-					uint32_t run, d;
-					if (phase == 0) { run = i; d = 0; }
-					else { const uint32_t it = s_res[wid][i]; run = it >> 8; d = it & 0xFFu; }
+			for (uint32_t b0 = 0; b0 < n_res; b0 += 32) {
+				const uint32_t j = b0 + lane;
+				if (j < n_res) {
+					const uint32_t i = s_res[wid][j];
+					const uint32_t run = run_of(s_incl[wid], i);
+					const uint32_t d = i - (run ? s_incl[wid][run - 1] : 0u);
 					const uint32_t mn = s_mn[wid][run];
 					const uint64_t f = rec_kmer(s_w[wid][run], d, k), rc = rc64(f, k);
-					const uint64_t x = f < rc ? f : rc;
 					uint64_t T = 0;
-					const bool pass = !(phase == 0 && filter_anchors) || filter_maybe(I, x);
-					const int64_t idr = pass ? lookup_one<SMALL>(I, x, mn, &T) : -1;
+					const int64_t idr = lookup_one<SMALL>(I, f < rc ? f : rc, mn, &T);
 					if (idr >= 0) found++; else notfound++;
-					if (WANT_IDS) A.out[s_src[wid][run]][s_o[ow][run] + d] = idr;
-					if (phase == 0) {
+					if (WANT_IDS) s_ids[iw][i] = (uint32_t)idr;  // -1 -> kIdAbsent; ids < 2^32 - 1 (the table exists)
+					if (d == 0) {
 						uint32_t flag = 0, dmax = 0;
 						if (idr >= 0) {
 							const bool same = window_at(I.seq, T, k) == f;
@@ -358,7 +363,51 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 					}
 				}
 			}
+			n_res = 0;
+			anchors = false;
 			__syncwarp();
+			// fill: every other k-mer of a run against the one window next to where the first one matched
+			#pragma unroll 1
+			while (base < n_ids && n_res + 32 <= (uint32_t)kResCap) {
+				const uint32_t i = base + lane;
+				bool left = false;
+				if (i < n_ids) {
+					const uint32_t run = run_of(s_incl[wid], i);
+					const uint32_t d = i - (run ? s_incl[wid][run - 1] : 0u);
+					if (d) {
+						left = true;
+						const uint32_t flag = s_flag[wid][run];
+						if ((flag & 1) && d <= s_dmax[wid][run]) {
+							const bool same = flag & 2;
+							const uint64_t Ta = s_T[wid][run];
+							const uint64_t Tp = same ? Ta + d : Ta - d;
+							const uint64_t f = rec_kmer(s_w[wid][run], d, k), rc = rc64(f, k);
+							if (window_at(I.seq, Tp, k) == (same ? f : rc)) {
+								left = false;
+								bool v;
+								if (WANT_IDS) {
+									const uint32_t pid = __ldg(I.pos_id + Tp);
+									v = pid != kIdAbsent;
+									s_ids[iw][i] = pid;
+								} else {
+									v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
+								}
+								if (v) found++; else notfound++;
+							}
+						}
+					}
+				}
+				const uint32_t lm = __ballot_sync(0xffffffffu, left);
+				if (left) s_res[wid][n_res + __popc(lm & lt_mask)] = (uint16_t)i;
+				n_res += __popc(lm);
+				base += 32;
+			}
+			__syncwarp();
+		} while (n_res > 0 || base < n_ids);
+		if (WANT_IDS) {
+			// the warp's answers back to the source: one contiguous stream of 32-bit ids over NVLink
+			uint32_t* dst = A.ret[src] + ko0;
+			for (uint32_t t = lane; t < n_ids; t += 32) dst[t] = s_ids[iw][t];
 		}
 	}
 	#pragma unroll
@@ -369,6 +418,62 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 	if (lane == 0) {
 		if (found) atomicAdd((unsigned long long*)&ctr[BLIGHT_CTR_FOUND], (unsigned long long)found);
 		if (notfound) atomicAdd((unsigned long long*)&ctr[BLIGHT_CTR_NOT_FOUND], (unsigned long long)notfound);
+	}
+}
+
+// Source side, after the owners answered: return streams -> int64 ids in read order. A warp takes 32 consecutive
+// records of one owner from the side table; their ids are consecutive in that owner's return region.
+__global__ void __launch_bounds__(kThreads) k_scatter_runs(const uint4* __restrict__ side, uint64_t cap, const unsigned long long* __restrict__ counts,
+                                                           const uint32_t* __restrict__ ret, uint64_t kcap, uint32_t world,
+                                                           int64_t* __restrict__ out) {
+	__shared__ unsigned long long s_pref[kMaxRanks + 1];
+	__shared__ unsigned long long s_cnt[kMaxRanks];
+	__shared__ uint64_t s_o[kWarps][32];
+	__shared__ uint16_t s_incl[kWarps][32];
+	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if (threadIdx.x == 0) {
+		unsigned long long acc = 0;
+		for (uint32_t d = 0; d < world; d++) {
+			const unsigned long long c = min(counts[d] >> kKmerBits, (unsigned long long)cap);
+			s_cnt[d] = c;
+			s_pref[d] = acc;
+			acc += (c + 31) / 32;
+		}
+		s_pref[world] = acc;
+	}
+	__syncthreads();
+	const uint64_t n_chunks = s_pref[world];
+	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
+	for (uint64_t chunk = (uint64_t)blockIdx.x * kWarps + wid; chunk < n_chunks; chunk += warp_stride) {
+		uint32_t d = 0;
+		while (d + 1 < world && chunk >= s_pref[d + 1]) d++;
+		const uint64_t rec0 = (chunk - s_pref[d]) * 32;
+		const uint32_t n_first = (uint32_t)min((unsigned long long)32, s_cnt[d] - rec0);
+		__syncwarp();
+		uint32_t n = 0, ko = 0;
+		if (lane < n_first) {
+			const uint4 e = __ldcs(side + (uint64_t)d * cap + rec0 + lane);
+			s_o[wid][lane] = ((uint64_t)e.y << 32) | e.x;
+			ko = e.z;
+			n = e.w;
+		}
+		uint32_t incl = n;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= (uint32_t)o) incl += t;
+		}
+		s_incl[wid][lane] = (uint16_t)incl;
+		const uint32_t n_ids = __shfl_sync(0xffffffffu, incl, 31);
+		const uint32_t ko0 = __shfl_sync(0xffffffffu, ko, 0);
+		__syncwarp();
+		const uint32_t* srcp = ret + (uint64_t)d * kcap + ko0;
+		for (uint32_t i = lane; i < n_ids; i += 32) {
+			const uint32_t run = run_of(s_incl[wid], i);
+			const uint32_t dd = i - (run ? s_incl[wid][run - 1] : 0u);
+			const uint32_t v = __ldcs(srcp + i);
+			__stcs(reinterpret_cast<long long*>(out + s_o[wid][run] + dd), v == kIdAbsent ? -1ll : (long long)v);
+		}
 	}
 }
 
@@ -385,6 +490,12 @@ int per_sm(K kernel) {
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
 	return nb;
 }
+
+struct DeviceGuardLite {
+	int prev = -1;
+	explicit DeviceGuardLite(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+	~DeviceGuardLite() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int finish(const char* what) {
 	cudaError_t e = cudaGetLastError();
@@ -405,12 +516,15 @@ int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint
 	if (!route || !d_counts || !d_ctr || !d_err || (n_reads && (!d_bases || !d_read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (route->world == 0 || route->world > (uint32_t)kMaxRanks || route->rank >= route->world) return fail(BL_ERR_INVALID_ARG, "bad world / rank");
 	if (k < 8 || k > 32 || m >= k || k - m + 1 < 8 || k - m + 1 > 32) return fail(BL_ERR_INVALID_ARG, "partition mode needs 8 <= k <= 32 and 8 <= k-m+1 <= 32");
+	if (route->cap == 0 || route->cap >= (1ull << 24) || route->kcap >= (1ull << 32)) return fail(BL_ERR_INVALID_ARG, "region capacities: cap < 2^24 records, kcap < 2^32 k-mers");
+	if (d_kmer_off && !route->side) return fail(BL_ERR_INVALID_ARG, "id mode needs the side table");
 	if (n_reads == 0 || total_bases == 0) return BL_OK;
 	if (pos_end > total_bases) pos_end = total_bases;
 	if (pos_begin >= pos_end) return BL_OK;
 	if ((pos_begin % kStrip) != 0 || (pos_end < total_bases && (pos_end % kStrip) != 0)) return fail(BL_ERR_INVALID_ARG, "sub-batch bounds must be multiples of 256");
 	Route R{};
-	R.world = route->world; R.rank = route->rank; R.lb = route->lb; R.cap = route->cap;
+	R.world = route->world; R.rank = route->rank; R.lb = route->lb; R.cap = route->cap; R.kcap = route->kcap;
+	R.side = static_cast<uint4*>(route->side);
 	for (uint32_t i = 0; i <= route->world; i++) R.cuts[i] = route->cuts[i];
 	for (uint32_t i = 0; i < route->world; i++) {
 		if (!route->inbox[i]) return fail(BL_ERR_INVALID_ARG, "null inbox pointer");
@@ -435,21 +549,22 @@ int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint
 	return finish("k_dispatch_runs");
 }
 
-int blight_part_lookup(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts, int64_t* const* out,
+int blight_part_lookup(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts, void* const* ret,
                        uint64_t max_records, uint64_t* d_ctr, void* stream) {
 	if (!idx || !regions || !d_counts || !d_ctr) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (world == 0 || world > (uint32_t)kMaxRanks) return fail(BL_ERR_INVALID_ARG, "bad world");
 	if (!idx->v.valid) return fail(BL_ERR_INVALID_ARG, "index has no valid-window bitmap");
-	if (out && !idx->v.pos_id) return fail(BL_ERR_INVALID_ARG, "id mode of the partitioned path needs the position->id table (BLIGHT_POS_ID)");
+	if (ret && !idx->v.pos_id) return fail(BL_ERR_INVALID_ARG, "id mode of the partitioned path needs the position->id table (BLIGHT_POS_ID)");
 	if (idx->v.k < 8) return fail(BL_ERR_INVALID_ARG, "partition mode needs k >= 8");
+	DeviceGuardLite guard(idx->device);
 	OwnerArgs A{};
 	A.world = world;
 	for (uint32_t i = 0; i < world; i++) {
 		A.region[i] = static_cast<const RunRec*>(regions[i]);
-		A.out[i] = out ? out[i] : nullptr;
+		A.ret[i] = ret ? static_cast<uint32_t*>(ret[i]) : nullptr;
 	}
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	const uint64_t want = std::max<uint64_t>(1, ((max_records + 31) / 32 + kWarps - 1) / kWarps);
+	const uint64_t want = std::max<uint64_t>(1, ((max_records + 31) / 32 + world + kWarps - 1) / kWarps);
 	const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(d_counts);
 #define BL_LAUNCH(IDS, SM)                                                                              \
 	do {                                                                                                 \
@@ -457,11 +572,23 @@ int blight_part_lookup(const blight_index* idx, uint32_t world, const void* cons
 		const uint64_t cap = (uint64_t)sm_count_() * nb;                                                 \
 		k_runs_lookup<IDS, SM><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(idx->v, A, cnt, d_ctr); \
 	} while (0)
-	if (out) { if (idx->v.small) BL_LAUNCH(true, true); else BL_LAUNCH(true, false); }
+	if (ret) { if (idx->v.small) BL_LAUNCH(true, true); else BL_LAUNCH(true, false); }
 	else { if (idx->v.small) BL_LAUNCH(false, true); else BL_LAUNCH(false, false); }
 #undef BL_LAUNCH
 	g_launches++;
 	return finish("k_runs_lookup");
+}
+
+int blight_part_scatter(const void* d_side, uint64_t cap, const uint64_t* d_counts, const void* d_ret, uint64_t kcap, uint32_t world,
+                        uint64_t max_records, int64_t* d_ids, void* stream) {
+	if (!d_side || !d_counts || !d_ret || !d_ids) return fail(BL_ERR_INVALID_ARG, "null argument");
+	if (world == 0 || world > (uint32_t)kMaxRanks) return fail(BL_ERR_INVALID_ARG, "bad world");
+	const uint64_t want = std::max<uint64_t>(1, ((max_records + 31) / 32 + world + kWarps - 1) / kWarps);
+	const uint64_t capb = (uint64_t)sm_count_() * 8;
+	k_scatter_runs<<<(unsigned)(want < capb ? want : capb), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+		static_cast<const uint4*>(d_side), cap, reinterpret_cast<const unsigned long long*>(d_counts), static_cast<const uint32_t*>(d_ret), kcap, world, d_ids);
+	g_launches++;
+	return finish("k_scatter_runs");
 }
 
 int blight_peer_alloc(uint64_t bytes, void** d_ptr, unsigned char* handle64) {

@@ -203,72 +203,78 @@ class PartitionedSet:
         return cls(PartitionPlan(list(cuts), lb), local, device, k, m, group)
 
     # ---- fused path: peer-memory stores inside the kernels -------------------------------------------------------
-    def enable_fused(self, max_kmers: int = 0, sub_positions: int = 16 << 20, records_per_position: float = 0.25):
-        """Allocates and exchanges the peer buffers: an inbox of 2 (double buffer) x world regions of `cap` records, and
-        (max_kmers > 0) an id buffer of max_kmers int64 that the owners write into. sub_positions = base positions per
-        sub-batch (one dispatch + one lookup kernel each)."""
+    def enable_fused(self, want_ids: bool = True, sub_positions: int = 16 << 20, records_per_position: float = 0.25):
+        """Allocates and exchanges the peer buffers. Per rank, double buffered: an inbox of world regions of `cap` records
+        (written by the sources), and for the id mode a return area of world regions of `sub_positions` 32-bit ids
+        (written by the owners) plus the local side table. sub_positions = base positions per sub-batch (one dispatch,
+        one lookup and one scatter kernel each)."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         dev = torch.device("cuda", self.index.device)
         self._sub = max(256, (int(sub_positions) // 256) * 256)
-        self._cap = max(1024, int(self._sub * records_per_position))
-        self._world, self._rank = world, rank
+        self._cap = min(max(1024, int(self._sub * records_per_position)), (1 << 24) - 1)
+        self._kcap = self._sub
+        self._world, self._rank, self._fused_ids = world, rank, want_ids
         region_bytes = self._cap * api.RUN_RECORD_BYTES
+        ret_bytes = self._kcap * 4
         self._inbox = api.PeerBuffer.alloc(2 * world * region_bytes)
-        self._ids = api.PeerBuffer.alloc(max(int(max_kmers), 1) * 8) if max_kmers > 0 else None
-        self._ids_cap = int(max_kmers)
-        mine = (self._inbox.handle, self._ids.handle if self._ids else b"", self._ids_cap)
+        self._ret = api.PeerBuffer.alloc(2 * world * ret_bytes) if want_ids else None
+        self._side = torch.empty(2 * world * self._cap * 16, dtype=torch.uint8, device=dev) if want_ids else None
+        mine = (self._inbox.handle, self._ret.handle if self._ret else b"")
         everyone = [None] * world
         if world > 1:
             dist.all_gather_object(everyone, mine, group=self.group)
         else:
             everyone = [mine]
         self._peers = []  # keep the mappings alive
-        inbox_ptr, ids_ptr = [0] * world, [0] * world
-        for r, (hi, hd, cap_r) in enumerate(everyone):
+        inbox_ptr, ret_ptr = [0] * world, [0] * world
+        for r, (hi, hr) in enumerate(everyone):
             if r == rank:
-                inbox_ptr[r], ids_ptr[r] = self._inbox.ptr, (self._ids.ptr if self._ids else 0)
+                inbox_ptr[r], ret_ptr[r] = self._inbox.ptr, (self._ret.ptr if self._ret else 0)
                 continue
             pb = api.PeerBuffer.open(hi, 2 * world * region_bytes)
             self._peers.append(pb)
             inbox_ptr[r] = pb.ptr
-            if hd:
-                pd = api.PeerBuffer.open(hd, cap_r * 8)
-                self._peers.append(pd)
-                ids_ptr[r] = pd.ptr
-        self._peer_ids = ids_ptr
-        self._routes, self._regions = [], []
+            if hr:
+                pr = api.PeerBuffer.open(hr, 2 * world * ret_bytes)
+                self._peers.append(pr)
+                ret_ptr[r] = pr.ptr
+        self._routes, self._regions, self._ret_at, self._ret_mine, self._side_at = [], [], [], [], []
         for b in range(2):
             rt = api.PartRoute()
-            rt.world, rt.rank, rt.lb, rt.cap = world, rank, self.plan.lb, self._cap
+            rt.world, rt.rank, rt.lb, rt.cap, rt.kcap = world, rank, self.plan.lb, self._cap, self._kcap
             for i, c in enumerate(self.plan.cuts):
                 rt.cuts[i] = c
             for d in range(world):  # my region in owner d's inbox: [buffer b][source = me]
                 rt.inbox[d] = inbox_ptr[d] + (b * world + rank) * region_bytes
+            side_b = (self._side.data_ptr() + b * world * self._cap * 16) if want_ids else 0
+            rt.side = side_b
             self._routes.append(rt)
+            self._side_at.append(side_b)
             self._regions.append([self._inbox.ptr + (b * world + s_) * region_bytes for s_ in range(world)])
+            # where I, as an owner, return ids to source s: [buffer b][owner = me] of s's return area; and my own area
+            self._ret_at.append([ret_ptr[s_] + (b * world + rank) * ret_bytes for s_ in range(world)] if want_ids else None)
+            self._ret_mine.append((self._ret.ptr + b * world * ret_bytes) if want_ids else 0)
         self._counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
         self._recv_counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         if world > 1:
             dist.barrier(group=self.group)
 
-    def ids_view(self, total_kmers: int) -> torch.Tensor:
-        """The first total_kmers ids of this rank's id buffer (written by the owners; valid after query_reads_fused returns
-        and until the next call)."""
-        dev = torch.device("cuda", self.index.device)
-        return self._ids.tensor(torch.int64, dev)[:total_kmers]
-
     def query_reads_fused(self, bases: torch.Tensor, read_off: torch.Tensor, kmer_off: Optional[torch.Tensor] = None,
-                          total_kmers: int = 0, want_ids: bool = True, check_overflow: bool = True):
+                          total_kmers: int = 0, want_ids: bool = True, ids: Optional[torch.Tensor] = None, check_overflow: bool = True):
         """Reads held by THIS rank -> (ids in read order or None, GLOBAL counters [found, not_found, queries, invalid] summed
-        over all ranks). Collective: every rank of the group must call it, with the same want_ids."""
+        over all ranks). Collective: every rank of the group must call it, with the same want_ids. Per sub-batch i, on the
+        current stream: dispatch(i) -> all-to-all of the counters (publishes the records of i and, because every owner
+        finished lookup(i-1) before entering it, the ids of i-1) -> scatter(i-1) -> lookup(i)."""
         if not hasattr(self, "_inbox"):
             raise RuntimeError("call enable_fused() first")
         world = self._world
         dev = bases.device
-        if want_ids and (self._ids is None or total_kmers > self._ids_cap):
-            raise ValueError("enable_fused(max_kmers=...) is smaller than this batch")
+        if want_ids and not self._fused_ids:
+            raise ValueError("enable_fused(want_ids=False) was asked for")
+        if want_ids and ids is None:
+            ids = torch.empty(max(int(total_kmers), 1), dtype=torch.int64, device=dev)
         ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
         total = bases.numel()
         n_sub = (total + self._sub - 1) // self._sub
@@ -278,7 +284,11 @@ class PartitionedSet:
             n_sub = int(t.item())
         self._err.zero_()
         koff = kmer_off if want_ids else None
-        out_ptrs = self._peer_ids if want_ids else None
+        max_rec = world * self._cap
+
+        def scatter(b):
+            api.part_scatter(self._side_at[b], self._cap, self._counts[b], self._ret_mine[b], self._kcap, world, max_rec, ids)
+
         for i in range(n_sub):
             b = i & 1
             cnt, rcv = self._counts[b], self._recv_counts[b]
@@ -287,14 +297,18 @@ class PartitionedSet:
                 api.part_dispatch(self.k, self.m, bases, read_off, koff, self._routes[b], cnt, ctr, self._err,
                                   i * self._sub, min(total, (i + 1) * self._sub))
             if world > 1:
-                dist.all_to_all_single(rcv, cnt, group=self.group)  # the counts, and the barrier that publishes the records
+                dist.all_to_all_single(rcv, cnt, group=self.group)
             else:
                 rcv = cnt
-            api.part_lookup(self.index, self._regions[b], rcv, out_ptrs, world * self._cap, ctr)
+            if want_ids and i > 0:
+                scatter(b ^ 1)
+            api.part_lookup(self.index, self._regions[b], rcv, self._ret_at[b] if want_ids else None, max_rec, ctr)
         e = self._err.to(torch.int64)
         if world > 1:
             dist.all_reduce(e, op=dist.ReduceOp.MAX, group=self.group)
-            dist.all_reduce(ctr, group=self.group)  # also the barrier after which every id has landed
+            dist.all_reduce(ctr, group=self.group)  # also the barrier after which the last ids have landed
+        if want_ids and n_sub > 0:
+            scatter((n_sub - 1) & 1)
         if check_overflow:
             host = torch.cat([e, ctr]).cpu()
             if int(host[1 + api.CTR_INVALID]):
@@ -305,7 +319,7 @@ class PartitionedSet:
                     return self.index.query_reads(bases, read_off, kmer_off, total_kmers, want_ids=want_ids)
                 ids, c = self.query_reads(bases, read_off, kmer_off, total_kmers)
                 return (ids if want_ids else None), all_reduce_counters(c, self.group)
-        return (self.ids_view(total_kmers) if want_ids else None), ctr
+        return (ids[:total_kmers] if want_ids else None), ctr
 
     def query_kmers(self, canon: torch.Tensor, mini: torch.Tensor) -> torch.Tensor:
         return exchange_lookup(canon, mini, self.plan, lambda c, mn: self.index.query_kmers(c, mini=mn), self.group)

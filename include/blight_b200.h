@@ -166,21 +166,29 @@ typedef struct blight_part_route {
 	uint32_t reserved;
 	uint32_t cuts[BLIGHT_MAX_RANKS + 1]; /* rank r owns MPHF groups [cuts[r], cuts[r+1]) */
 	void* inbox[BLIGHT_MAX_RANKS];       /* DEVICE pointers: this source's region in every owner's inbox (peer memory) */
-	uint64_t cap;                        /* records per region */
+	uint64_t cap;                        /* records per region (< 2^24) */
+	uint64_t kcap;                       /* k-mers per return region (< 2^32) */
+	void* side;                          /* DEVICE, local: world * cap entries of 16 bytes (where each run's ids go); NULL in counting mode */
 } blight_part_route;
 
 /* Front end + dispatch of the k-mers starting in [pos_begin, pos_end) of a read batch (bounds: multiples of 256, or
- * the end). d_kmer_off == NULL: counting mode (records carry no output slot). d_counts[world] (records stored per
- * owner) is ACCUMULATED into; d_ctr gets BLIGHT_CTR_QUERIES / BLIGHT_CTR_INVALID; *d_err |= 1 if a region overflowed
- * (records beyond `cap` are dropped: the caller must retry with smaller sub-batches). */
+ * the end). d_kmer_off == NULL: counting mode. d_counts[world] is ACCUMULATED into: per owner, records stored << 40 |
+ * k-mers stored (zero it per sub-batch); d_ctr gets BLIGHT_CTR_QUERIES / BLIGHT_CTR_INVALID; *d_err |= 1 if a region
+ * overflowed (those records are dropped: the caller must retry with smaller sub-batches or another path). */
 int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
                          uint64_t n_reads, uint64_t total_bases, uint64_t pos_begin, uint64_t pos_end, const blight_part_route* route,
                          uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream);
-/* Owner side: regions[s] = records received from source s (device pointer), d_counts[s] = how many (DEVICE array, so
- * no host round trip), out[s] = id buffer of source s (peer pointer; out == NULL: counting mode). max_records bounds
- * the total for the grid size. d_ctr gets BLIGHT_CTR_FOUND / BLIGHT_CTR_NOT_FOUND (accumulated). */
+/* Owner side: regions[s] = records received from source s (device pointer), d_counts[s] = the packed counter source s
+ * accumulated for this owner (DEVICE array: no host round trip), ret[s] = this owner's return region at source s
+ * (peer pointer, 32-bit ids, 0xFFFFFFFF = -1; ret == NULL: counting mode). max_records bounds the total for the grid
+ * size. d_ctr gets BLIGHT_CTR_FOUND / BLIGHT_CTR_NOT_FOUND (accumulated). */
 int blight_part_lookup(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts,
-                       int64_t* const* out, uint64_t max_records, uint64_t* d_ctr, void* stream);
+                       void* const* ret, uint64_t max_records, uint64_t* d_ctr, void* stream);
+/* Back on the source, once every owner has answered: return regions (d_ret: world regions of kcap 32-bit ids, region d
+ * written by owner d) -> int64 ids at the slots query_sequence_hash would fill (blight.cpp:575-591), through the side
+ * table and the counters the dispatch left. */
+int blight_part_scatter(const void* d_side, uint64_t cap, const uint64_t* d_counts, const void* d_ret, uint64_t kcap, uint32_t world,
+                        uint64_t max_records, int64_t* d_ids, void* stream);
 /* Device buffers other processes of the box can map (CUDA IPC): alloc + 64-byte handle here, open there. */
 int blight_peer_alloc(uint64_t bytes, void** d_ptr, unsigned char* handle64);
 int blight_peer_open(const unsigned char* handle64, void** d_ptr);

@@ -38,7 +38,7 @@ def test_loopback_partition_matches_oracle(shape, tmp_path, torch_cuda):
     plan = bdist.PartitionPlan([0, info["n_mphf"]], 2 * m - 1 - n)
     ps = bdist.PartitionedSet(plan, flat, 0, 31, m)
     d_b, d_o, d_k, total = _dev_batch(torch, rb, ro)
-    ps.enable_fused(max_kmers=total, sub_positions=1 << 17)  # several sub-batches, both inbox buffers
+    ps.enable_fused(sub_positions=1 << 17)  # several sub-batches, both inbox buffers
     n0 = api.launch_count()
     ids, ctr = ps.query_reads_fused(d_b, d_o, d_k, total)
     torch.cuda.synchronize()
@@ -68,14 +68,14 @@ def test_loopback_ragged_and_tiny_reads(tmp_path, torch_cuda):
     plan = bdist.PartitionPlan([0, flat.info()["n_mphf"]], 2 * 9 - 1 - 6)
     ps = bdist.PartitionedSet(plan, flat, 0, 31, 9)
     d_b, d_o, d_k, total = _dev_batch(torch, rb, ro)
-    ps.enable_fused(max_kmers=total, sub_positions=1 << 16, records_per_position=1.0)
+    ps.enable_fused(sub_positions=1 << 16, records_per_position=1.0)
     ids, ctr = ps.query_reads_fused(d_b, d_o, d_k, total)
     torch.cuda.synchronize()
     assert np.array_equal(ids.cpu().numpy(), want)
     assert (int(ctr[0]), int(ctr[1])) == (int(wctr[0]), int(wctr[1]))
     # an inbox too small for the batch: detected, answered through the plain path, same ids
     ps2 = bdist.PartitionedSet(plan, flat, 0, 31, 9)
-    ps2.enable_fused(max_kmers=total, sub_positions=1 << 16, records_per_position=0.001)
+    ps2.enable_fused(sub_positions=1 << 16, records_per_position=0.001)
     ids2, ctr3 = ps2.query_reads_fused(d_b, d_o, d_k, total)
     torch.cuda.synchronize()
     assert np.array_equal(ids2.cpu().numpy()[:total], want)
@@ -104,31 +104,36 @@ def test_three_owners_two_sources_on_one_gpu(tmp_path, torch_cuda):
     for lo, hi in ((0, half), (half, len(ro) - 1)):
         o = ro[lo:hi + 1] - ro[lo]
         parts.append((rb[int(ro[lo]):int(ro[hi])], o, want[int(synth.kmer_offsets(ro, 31)[lo]):int(synth.kmer_offsets(ro, 31)[hi])]))
-    cap = 1 << 16
-    inbox = torch.zeros(world * world * cap * api.RUN_RECORD_BYTES, dtype=torch.uint8, device="cuda")  # [owner][source][cap]
-    counts = torch.zeros(world, world, dtype=torch.int64, device="cuda")                              # [source][owner]
+    cap, kcap = 1 << 16, 1 << 21
+    RB = api.RUN_RECORD_BYTES
+    inbox = torch.zeros(world * world * cap * RB, dtype=torch.uint8, device="cuda")   # [owner][source][cap]
+    ret = torch.zeros(2, world, kcap, dtype=torch.int32, device="cuda")               # [source][owner][kcap]
+    side = torch.zeros(2, world * cap * 16, dtype=torch.uint8, device="cuda")         # [source][owner][cap]
+    counts = torch.zeros(world, world, dtype=torch.int64, device="cuda")              # [source][owner], packed
     ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
-    ids_bufs, totals = [], []
+    ids_bufs = []
     for s, (pb, po, _) in enumerate(parts):
         d_b, d_o, d_k, total = _dev_batch(torch, pb, po)
         ids_bufs.append(torch.full((total,), -7, dtype=torch.int64, device="cuda"))
-        totals.append(total)
         rt = api.PartRoute()
-        rt.world, rt.rank, rt.lb, rt.cap = world, s, plan.lb, cap
+        rt.world, rt.rank, rt.lb, rt.cap, rt.kcap = world, s, plan.lb, cap, kcap
+        rt.side = side[s].data_ptr()
         for i, c in enumerate(plan.cuts):
             rt.cuts[i] = c
         for d in range(world):
-            rt.inbox[d] = inbox.data_ptr() + (d * world + s) * cap * api.RUN_RECORD_BYTES
+            rt.inbox[d] = inbox.data_ptr() + (d * world + s) * cap * RB
         api.part_dispatch(31, m, d_b, d_o, d_k, rt, counts[s], ctr, err)
     torch.cuda.synchronize()
     assert int(err.item()) == 0
-    out_ptrs = [ids_bufs[0].data_ptr(), ids_bufs[1].data_ptr(), 0]
     for d in range(world):
-        regions = [inbox.data_ptr() + (d * world + s) * cap * api.RUN_RECORD_BYTES for s in range(world)]
+        regions = [inbox.data_ptr() + (d * world + s) * cap * RB for s in range(world)]
         cnt_d = counts[:, d].contiguous()
         assert int(cnt_d[2]) == 0 and int(cnt_d[0]) > 0
-        api.part_lookup(owners[d], regions, cnt_d, out_ptrs, world * cap, ctr)
+        ret_ptrs = [ret[s, d].data_ptr() for s in range(2)] + [0]
+        api.part_lookup(owners[d], regions, cnt_d, ret_ptrs, world * cap, ctr)
+    for s in range(2):
+        api.part_scatter(side[s].data_ptr(), cap, counts[s], ret[s].data_ptr(), kcap, world, world * cap, ids_bufs[s])
     torch.cuda.synchronize()
     for s in range(2):
         assert np.array_equal(ids_bufs[s].cpu().numpy(), parts[s][2]), s

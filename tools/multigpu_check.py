@@ -98,8 +98,9 @@ def main():
     ok = True
 
     # partition mode, fused peer-memory path
-    part.enable_fused(max_kmers=total, sub_positions=sub)
+    part.enable_fused(sub_positions=sub)
     ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
+    ids_buf = torch.empty(total, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
     okf = torch.tensor([1 if torch.equal(ids_f, ids_rep) else 0], device=dev)
     dist.all_reduce(okf, op=dist.ReduceOp.MIN)
@@ -108,7 +109,7 @@ def main():
     out["fused_ids_equal_replica"] = bool(okf.item())
     out["fused_counters_equal_replica"] = bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]) and torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
     ok = ok and out["fused_ids_equal_replica"] and out["fused_counters_equal_replica"]
-    f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, check_overflow=False), reps, dev)
+    f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, ids=ids_buf, check_overflow=False), reps, dev)
     f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False), reps, dev)
     out.update({"fused_ids_ms": f_ids_ms, "fused_ids_kmers_per_s": world * total / (f_ids_ms * 1e-3),
                 "fused_count_ms": f_cnt_ms, "fused_count_kmers_per_s": world * total / (f_cnt_ms * 1e-3),
