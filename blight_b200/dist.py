@@ -203,16 +203,39 @@ class PartitionedSet:
         return cls(PartitionPlan(list(cuts), lb), local, device, k, m, group)
 
     # ---- fused path: peer-memory stores inside the kernels -------------------------------------------------------
-    def enable_fused(self, want_ids: bool = True, sub_positions: int = 16 << 20, records_per_position: float = 0.25):
+    def disable_fused(self):
+        """Unmaps the peers' buffers, then (after a barrier) frees this rank's."""
+        if not hasattr(self, "_inbox"):
+            return
+        torch.cuda.synchronize()
+        for pb in self._peers:
+            pb.close()
+        self._peers = []
+        if self._world > 1:
+            dist.barrier(group=self.group)
+        self._inbox.close()
+        if self._ret:
+            self._ret.close()
+        del self._inbox, self._ret, self._side
+
+    def enable_fused(self, want_ids: bool = True, sub_positions: int = 64 << 20, records_per_position: Optional[float] = None):
         """Allocates and exchanges the peer buffers. Per rank, double buffered: an inbox of world regions of `cap` records
         (written by the sources), and for the id mode a return area of world regions of `sub_positions` 32-bit ids
         (written by the owners) plus the local side table. sub_positions = base positions per sub-batch (one dispatch,
-        one lookup and one scatter kernel each)."""
+        one lookup and one scatter kernel each): at 64 M and 8 ranks that is 2 GB of inbox, 4 GB of return area and 1 GB
+        of side table per rank."""
+        self.disable_fused()
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         dev = torch.device("cuda", self.index.device)
-        self._sub = max(256, (int(sub_positions) // 256) * 256)
-        self._cap = min(max(1024, int(self._sub * records_per_position)), (1 << 24) - 1)
+        if records_per_position is None:
+            # a read batch has ~0.07 super-k-mers per base, spread over `world` owners; an overflow is detected and the
+            # batch answered through the plain path, so this only has to be generous, not safe
+            records_per_position = min(0.25, max(0.03, 0.5 / world))
+        max_cap = (1 << 24) - 1  # the packed (slots, k-mers) counter keeps 24 bits of slots
+        sub_positions = min(int(sub_positions), int(max_cap / records_per_position))
+        self._sub = max(256, (sub_positions // 256) * 256)
+        self._cap = min(max(1024, int(self._sub * records_per_position)), max_cap)
         self._kcap = self._sub
         self._world, self._rank, self._fused_ids = world, rank, want_ids
         region_bytes = self._cap * api.RUN_RECORD_BYTES
@@ -260,6 +283,10 @@ class PartitionedSet:
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         if world > 1:
             dist.barrier(group=self.group)
+
+    def overflowed(self) -> bool:
+        """True if the last query_reads_fused on this rank dropped records (only meaningful with check_overflow=False)."""
+        return bool(int(self._err.item()))
 
     def query_reads_fused(self, bases: torch.Tensor, read_off: torch.Tensor, kmer_off: Optional[torch.Tensor] = None,
                           total_kmers: int = 0, want_ids: bool = True, ids: Optional[torch.Tensor] = None, check_overflow: bool = True):

@@ -43,7 +43,7 @@ def main():
     genome_len = int(os.environ.get("BLIGHT_CHECK_GENOME", 20_000_000))
     n_reads = int(os.environ.get("BLIGHT_CHECK_READS", 2_000_000))
     m, n, b = (int(os.environ.get("BLIGHT_CHECK_" + x, d)) for x, d in (("M", 9), ("N", 10), ("B", 6)))
-    sub = int(os.environ.get("BLIGHT_CHECK_SUB", 16 << 20))
+    subs = [int(x) for x in os.environ.get("BLIGHT_CHECK_SUB", str(64 << 20)).split(",")]
     plain = os.environ.get("BLIGHT_CHECK_PLAIN", "1") != "0"
     reps = int(os.environ.get("BLIGHT_CHECK_REPS", 3))
     torch.cuda.set_device(local)
@@ -97,23 +97,34 @@ def main():
            "replica_count_ms": rep_cnt_ms, "replica_count_kmers_per_s": world * total / (rep_cnt_ms * 1e-3)}
     ok = True
 
-    # partition mode, fused peer-memory path
-    part.enable_fused(sub_positions=sub)
-    ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
+    # partition mode, fused peer-memory path (one pass per sub-batch size asked for; the last one is the headline)
     ids_buf = torch.empty(total, dtype=torch.int64, device=dev)
-    torch.cuda.synchronize()
-    okf = torch.tensor([1 if torch.equal(ids_f, ids_rep) else 0], device=dev)
-    dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-    _, ctr_c = part.query_reads_fused(bases, roff, want_ids=False)
-    torch.cuda.synchronize()
-    out["fused_ids_equal_replica"] = bool(okf.item())
-    out["fused_counters_equal_replica"] = bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]) and torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
+    out["fused_ids_equal_replica"] = out["fused_counters_equal_replica"] = True
+    out["fused_by_sub"] = {}
+    for sub in subs:
+        part.enable_fused(sub_positions=sub)
+        ids_buf.fill_(-7)
+        ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total, ids=ids_buf)
+        torch.cuda.synchronize()
+        okf = torch.tensor([1 if torch.equal(ids_f, ids_rep) else 0], device=dev)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        _, ctr_c = part.query_reads_fused(bases, roff, want_ids=False)
+        torch.cuda.synchronize()
+        out["fused_ids_equal_replica"] &= bool(okf.item())
+        out["fused_counters_equal_replica"] &= bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]) and torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
+        f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, ids=ids_buf, check_overflow=False), reps, dev)
+        f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False), reps, dev)
+        ovf = torch.tensor([1 if part.overflowed() else 0], device=dev)
+        dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
+        out["fused_by_sub"][str(part._sub)] = {"ids_ms": f_ids_ms, "count_ms": f_cnt_ms, "overflow": bool(ovf.item())}
+        ok = ok and not bool(ovf.item())
+        out.update({"fused_sub_positions": part._sub, "fused_ids_ms": f_ids_ms, "fused_ids_kmers_per_s": world * total / (f_ids_ms * 1e-3),
+                    "fused_count_ms": f_cnt_ms, "fused_count_kmers_per_s": world * total / (f_cnt_ms * 1e-3),
+                    "found_total": int(ctr_f[0]), "replica_found_total": int(ctr_all[0])})
     ok = ok and out["fused_ids_equal_replica"] and out["fused_counters_equal_replica"]
-    f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, ids=ids_buf, check_overflow=False), reps, dev)
-    f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False), reps, dev)
-    out.update({"fused_ids_ms": f_ids_ms, "fused_ids_kmers_per_s": world * total / (f_ids_ms * 1e-3),
-                "fused_count_ms": f_cnt_ms, "fused_count_kmers_per_s": world * total / (f_cnt_ms * 1e-3),
-                "found_total": int(ctr_f[0]), "replica_found_total": int(ctr_all[0])})
+    out["fused_ids_vs_one_gpu"] = out["fused_ids_kmers_per_s"] / (total / (rep_ids_ms * 1e-3))
+    out["fused_count_vs_one_gpu"] = out["fused_count_kmers_per_s"] / (total / (rep_cnt_ms * 1e-3))
+    part.disable_fused()
 
     # partition mode, plain NCCL exchange of (canon, minimizer) pairs
     if plain:
