@@ -281,6 +281,9 @@ class PartitionedSet:
         self._counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
         self._recv_counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._side_stream = torch.cuda.Stream(device=dev)
+        self._ev_pub = torch.cuda.Event()
+        self._ev_scat = [torch.cuda.Event(), torch.cuda.Event()]
         if world > 1:
             dist.barrier(group=self.group)
 
@@ -302,6 +305,8 @@ class PartitionedSet:
             raise ValueError("enable_fused(want_ids=False) was asked for")
         if want_ids and ids is None:
             ids = torch.empty(max(int(total_kmers), 1), dtype=torch.int64, device=dev)
+        if want_ids:
+            ids.record_stream(self._side_stream)
         ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
         total = bases.numel()
         n_sub = (total + self._sub - 1) // self._sub
@@ -313,12 +318,23 @@ class PartitionedSet:
         koff = kmer_off if want_ids else None
         max_rec = world * self._cap
 
-        def scatter(b):
-            api.part_scatter(self._side_at[b], self._cap, self._counts[b], self._ret_mine[b], self._kcap, world, max_rec, ids)
+        main = torch.cuda.current_stream()
+        side = self._side_stream
 
+        def scatter(b):
+            # on a second stream, next to the lookup of the following sub-batch (it only moves bytes)
+            self._ev_pub.record(main)
+            side.wait_event(self._ev_pub)
+            api.part_scatter(self._side_at[b], self._cap, self._counts[b], self._ret_mine[b], self._kcap, world, max_rec, ids, stream=side)
+            self._ev_scat[b].record(side)
+
+        pending = [False, False]
         for i in range(n_sub):
             b = i & 1
             cnt, rcv = self._counts[b], self._recv_counts[b]
+            if pending[b]:
+                main.wait_event(self._ev_scat[b])  # the scatter of sub-batch i-2 still reads this buffer's counters and side table
+                pending[b] = False
             cnt.zero_()
             if i * self._sub < total:
                 api.part_dispatch(self.k, self.m, bases, read_off, koff, self._routes[b], cnt, ctr, self._err,
@@ -329,6 +345,7 @@ class PartitionedSet:
                 rcv = cnt
             if want_ids and i > 0:
                 scatter(b ^ 1)
+                pending[b ^ 1] = True
             api.part_lookup(self.index, self._regions[b], rcv, self._ret_at[b] if want_ids else None, max_rec, ctr)
         e = self._err.to(torch.int64)
         if world > 1:
@@ -336,6 +353,10 @@ class PartitionedSet:
             dist.all_reduce(ctr, group=self.group)  # also the barrier after which the last ids have landed
         if want_ids and n_sub > 0:
             scatter((n_sub - 1) & 1)
+            pending[(n_sub - 1) & 1] = True
+        for b in range(2):
+            if pending[b]:
+                main.wait_event(self._ev_scat[b])
         if check_overflow:
             host = torch.cat([e, ctr]).cpu()
             if int(host[1 + api.CTR_INVALID]):
