@@ -62,9 +62,14 @@ def b_alg(b: int, k: int = 31) -> float:
     return 32.0 * (1.65 + 1 + 1 + seq_sectors) + 1.25 + 8.0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this exact
-# workload (profiles/r01_v5_sk_count_ncu.txt, profiles/r01_v3_kreads_ncu.txt); None for any other configuration.
-NCU_TRAFFIC_BYTES = {"k_reads_sk<count>": 99.76e9, "k_reads<ids>": 209.1e9}
+def ncu_traffic(kname: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel, from the committed `ncu --set full`
+    capture of this exact workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kname, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -187,7 +192,7 @@ def workload_config(args, world):
         "k": args.k, "m": args.m, "n": args.n, "s": args.s, "b": args.b,
         "kmers_per_step_per_gpu": args.reads * (args.read_len - args.k + 1),
         "parallelism": f"replica x{world}, reads sharded, no data-path collective",
-        "cache": "inputs (1.5 GB of reads per step) and the index (349 MB) exceed the 126 MB L2; no explicit flush",
+        "cache": "inputs (1.5 GB of reads per step) and the index (1.8 GB in HBM) exceed the 126 MB L2; no explicit flush",
     }
 
 
@@ -341,7 +346,7 @@ def main():
         achieved = balg * total_kmers / (kernel_ms * 1e-3) / 1e9
         kname = "k_reads_sk<ids>" if headline_ids else "k_reads_sk<count>"
         default_cfg = (args.genome, args.reads, args.read_len, args.k, args.m, args.n, args.b) == (100_000_000, 10_000_000, 150, 31, 7, 5, 6)
-        traffic = NCU_TRAFFIC_BYTES.get(kname) if default_cfg else None
+        traffic = ncu_traffic(kname) if default_cfg else None
         line = {
             "metric": "queried k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -60,4 +60,11 @@ lines += ["", "## top source lines by executed warp instructions (share of instr
 for a in sorted(agg, key=lambda a: -a[4])[:30]:
     lines.append(f"{a[0]}:{a[1]:<4d} {100 * a[4] / ti:5.1f}% {100 * a[3] / ts:5.1f}% {a[5] / max(a[4], 1):5.1f}  {a[2][:95]}")
 open(out, "w").write("\n".join(lines) + "\n")
+if len(sys.argv) > 4:
+    # usage: ... kmers_per_launch kernel_key  -> records the DRAM traffic bench.py reports as roofline.traffic
+    import json, os
+    tf = os.path.join(os.path.dirname(os.path.abspath(out)), "ncu_traffic.json")
+    d = json.load(open(tf)) if os.path.exists(tf) else {}
+    d[sys.argv[4]] = {"dram_bytes_per_launch": dr + dw, "source": os.path.basename(out), "kmers_per_launch": kmers}
+    json.dump(d, open(tf, "w"), indent=1, sort_keys=True)
 print("\n".join(lines[:40]))

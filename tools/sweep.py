@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """BASELINE.json configs[2]: b sweep 0-8 and m sweep {7,9,11} on the 100 M-k-mer synthetic index, one GPU.
-For every shape: throughput (hash mode, CUDA events, inputs resident) and a parity check of a read sample against the
+For every shape: throughput (id mode and counting mode, CUDA events, inputs resident) and a parity check of a read sample against the
 oracle (C port). Prints one JSON line per shape; profiles/ keeps the table."""
 import json
 import os
@@ -49,6 +49,15 @@ for (m, n, b) in shapes:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    e0.record()
+    for _ in range(reps):
+        idx.query_reads(bases, roff, want_ids=False, ctr=ctr)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_count = e0.elapsed_time(e1) / reps
+    ctr.zero_()
+    idx.query_reads(bases, roff, koff, n_reads * 120, ids=ids, ctr=ctr)
+    torch.cuda.synchronize()
     with tempfile.TemporaryDirectory() as td:
         blob = os.path.join(td, "x.blflat")
         flat.save(blob)
@@ -57,6 +66,7 @@ for (m, n, b) in shapes:
     got = ids[: sample * 120].cpu().numpy()
     info = idx.info
     print(json.dumps({"k": 31, "m": m, "n": n, "b": b, "kmers_per_s": n_reads * 120 / (ms * 1e-3), "ms": ms,
+                      "count_kmers_per_s": n_reads * 120 / (ms_count * 1e-3), "count_ms": ms_count,
                       "parity_sample_kmers": int(len(want)), "parity_ok": bool(np.array_equal(got, want)),
                       "oracle_found": int(wctr[0]), "found_fraction": float(ctr[0]) / float(ctr[2]),
                       "device_MB": info["device_bytes"] / 1e6, "bits_per_kmer": 8.0 * info["device_bytes"] / info["number_kmer"],
