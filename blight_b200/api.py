@@ -27,7 +27,7 @@ SYMBOLS = [
     "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
-    "blight_part_dispatch", "blight_part_lookup", "blight_part_scatter", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
+    "blight_consume_reads", "blight_gather_reads", "blight_part_dispatch", "blight_part_lookup", "blight_part_scatter", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
 ]
 MAX_RANKS = 16
 RUN_RECORD_BYTES = 32
@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
     L.blight_owner_scatter.argtypes = [vp, vp, u64, vp, u32, u32, vp, vp, vp, vp, vp]
     L.blight_scatter_ids.argtypes = [vp, vp, u64, vp, vp]
     L.blight_launch_count.restype = u64
+    L.blight_consume_reads.argtypes = [vp, vp, vp, u64, u64, C.c_int, vp, u32, u32, vp, vp]
+    L.blight_gather_reads.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp]
     L.blight_part_dispatch.argtypes = [u32, u32, vp, vp, vp, u64, u64, u64, u64, C.POINTER(PartRoute), vp, vp, vp, vp]
     L.blight_part_lookup.argtypes = [vp, u32, C.POINTER(vp), vp, C.POINTER(vp), u64, vp, vp]
     L.blight_part_scatter.argtypes = [vp, u64, vp, vp, u64, u32, u64, vp, vp]
@@ -260,6 +262,36 @@ class DeviceIndex:
         _check(lib().blight_query_reads(self._h, _ptr(bases), _ptr(read_off), _ptr(kmer_off), n_reads, bases.numel(),
                                         int(total_kmers), _ptr(ids) if want_ids else 0, _ptr(ctr), _stream_handle(stream)))
         return (ids if want_ids else None), ctr
+
+    # -- id consumers fused behind the lookup (the reference's snippet applications) -------------------------
+    def count_reads(self, bases, read_off, table, ctr=None, stream=None):
+        """table[id] += 1 (uint32/int32 CUDA tensor of number_kmer entries) for every k-mer of every read: abundance[id]++."""
+        import torch
+        if ctr is None:
+            ctr = torch.zeros(N_CTR, dtype=torch.int64, device=bases.device)
+        _check(lib().blight_consume_reads(self._h, _ptr(bases), _ptr(read_off), read_off.numel() - 1, bases.numel(), 0, _ptr(table), 0, 0,
+                                          _ptr(ctr), _stream_handle(stream)))
+        return ctr
+
+    def color_reads(self, bases, read_off, bits, n_colors: int, color: int, ctr=None, stream=None):
+        """Sets bit id * n_colors + color of `bits` (int32 CUDA tensor of ceil(number_kmer * n_colors / 32) words)."""
+        import torch
+        if ctr is None:
+            ctr = torch.zeros(N_CTR, dtype=torch.int64, device=bases.device)
+        _check(lib().blight_consume_reads(self._h, _ptr(bases), _ptr(read_off), read_off.numel() - 1, bases.numel(), 1, _ptr(bits), n_colors,
+                                          color, _ptr(ctr), _stream_handle(stream)))
+        return ctr
+
+    def gather_reads(self, bases, read_off, kmer_off, total_kmers, table, out=None, ctr=None, stream=None):
+        """out[kmer_off[r] + pos] = table[id] (0xFFFFFFFF = -1 as int32 for absent k-mers)."""
+        import torch
+        if ctr is None:
+            ctr = torch.zeros(N_CTR, dtype=torch.int64, device=bases.device)
+        if out is None:
+            out = torch.empty(max(int(total_kmers), 1), dtype=torch.int32, device=bases.device)
+        _check(lib().blight_gather_reads(self._h, _ptr(bases), _ptr(read_off), _ptr(kmer_off), read_off.numel() - 1, bases.numel(),
+                                         _ptr(table), _ptr(out), _ptr(ctr), _stream_handle(stream)))
+        return out[:total_kmers], ctr
 
     # -- host buffers ------------------------------------------------------------------------------------
     def query_fasta_host(self, text) -> np.ndarray:

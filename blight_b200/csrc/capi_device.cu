@@ -241,6 +241,7 @@ void blight_index_free(blight_index* idx) {
 	cudaFree(idx->d_bucket); cudaFree(idx->d_mphf); cudaFree(idx->d_bits); cudaFree(idx->d_pos); cudaFree(idx->d_seq);
 	cudaFree(idx->d_fbk); cudaFree(idx->d_fbv); cudaFree(idx->d_valid); cudaFree(idx->d_pos_id); cudaFree(idx->d_filter);
 	for (void* w : idx->ws) cudaFree(w);
+	if (idx->stream_ctx) stream_ctx_free(idx->stream_ctx);
 	if (idx->host_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->host_stream));
 	if (idx->copy_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->copy_stream));
 	if (idx->ev_copy) cudaEventDestroy(static_cast<cudaEvent_t>(idx->ev_copy));
@@ -293,6 +294,28 @@ int blight_query_reads(const blight_index* idx, const char* d_bases, const uint6
 	DeviceGuard guard(idx->device);
 	int rc = launch_reads(&idx->v, idx->v.k, idx->v.m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, nullptr, nullptr,
 	                      d_ids, d_ctr, static_cast<cudaStream_t>(stream));
+	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+}
+
+int blight_consume_reads(const blight_index* idx, const char* d_bases, const uint64_t* d_read_off, uint64_t n_reads, uint64_t total_bases,
+                         int kind, uint32_t* d_table, uint32_t n_colors, uint32_t color, uint64_t* d_ctr, void* stream) {
+	if (!idx || !d_table || !d_ctr || (n_reads && (!d_bases || !d_read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	if (kind != BLIGHT_CONSUME_COUNT && kind != BLIGHT_CONSUME_COLOR) return fail(BL_ERR_INVALID_ARG, "unknown consumer");
+	if (kind == BLIGHT_CONSUME_COLOR && (n_colors == 0 || color >= n_colors)) return fail(BL_ERR_INVALID_ARG, "color out of range");
+	if (!idx->v.pos_id || idx->v.k - idx->v.m + 1 < 8) return fail(BL_ERR_INVALID_ARG, "the fused consumers need the position->id table (N < 2^32-1, BLIGHT_POS_ID) and k-m+1 >= 8");
+	DeviceGuard guard(idx->device);
+	int rc = launch_reads_sink(idx->v, kind, d_bases, d_read_off, nullptr, n_reads, total_bases, d_table, n_colors, color, nullptr, d_ctr,
+	                           static_cast<cudaStream_t>(stream));
+	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+}
+
+int blight_gather_reads(const blight_index* idx, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off, uint64_t n_reads,
+                        uint64_t total_bases, const uint32_t* d_table, uint32_t* d_out, uint64_t* d_ctr, void* stream) {
+	if (!idx || !d_table || !d_out || !d_ctr || (n_reads && (!d_bases || !d_read_off || !d_kmer_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	if (!idx->v.pos_id || idx->v.k - idx->v.m + 1 < 8) return fail(BL_ERR_INVALID_ARG, "the fused consumers need the position->id table (N < 2^32-1, BLIGHT_POS_ID) and k-m+1 >= 8");
+	DeviceGuard guard(idx->device);
+	int rc = launch_reads_sink(idx->v, 2, d_bases, d_read_off, d_kmer_off, n_reads, total_bases, const_cast<uint32_t*>(d_table), 0, 0, d_out, d_ctr,
+	                           static_cast<cudaStream_t>(stream));
 	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
 }
 
@@ -386,6 +409,10 @@ int blight_query_fasta_host(const blight_index* idx, const char* text, uint64_t 
 
 int blight_query_file_host(const blight_index* idx, const char* path, uint64_t* ctr) {
 	if (!idx || !ctr || !path) return fail(BL_ERR_INVALID_ARG, "null argument");
+	{
+		const char* e = getenv("BLIGHT_FILE_QUERY");  // "whole": read the file into memory first (tests compare the two)
+		if (!e || e[0] != 'w') return stream_file_query(idx, path, ctr);
+	}
 	std::string storage, err;
 	std::vector<SeqView> recs;
 	int rc = read_fasta_records(path, storage, recs, &err);

@@ -90,6 +90,7 @@ struct blight_index {
 	void* ev_copy = nullptr;
 	void* ev_ws = nullptr;
 	void* host_mutex = nullptr;
+	void* stream_ctx = nullptr;   // pinned / device buffers of the streaming file_query (stream_query.cu), created on first use
 	void* ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // grow-only scratch of the *_host entry points
 	size_t ws_cap[6] = {0, 0, 0, 0, 0, 0};
 };

@@ -75,7 +75,28 @@ __global__ void __launch_bounds__(kThreads) k_window_valid(DevIndexView I, uint6
 	}
 }
 
-enum ReadsMode { kEmitPairs = 0, kLookupIds = 1, kLookupCount = 2 };
+enum ReadsMode { kEmitPairs = 0, kLookupIds = 1, kLookupCount = 2, kConsumeCount = 3, kConsumeColor = 4, kGatherTable = 5 };
+
+// Where the identifier of a k-mer goes (k_reads_sk). Besides the id array of query_sequence_hash, the consumers the
+// reference's applications put behind it (Abundance_De_Bruijn_graph_snippet.cpp:118-151, Colored_…:117-151), fused so
+// that ids never leave the GPU: abundance[id]++, color[id * n_colors + c] = true, and the read-side gather abundance[id].
+struct Sink {
+	int64_t* ids;       // kLookupIds: ids[o] = id
+	uint32_t* table;    // kConsumeCount: table[id] += 1; kConsumeColor: bit id * n_colors + color set; kGatherTable: read
+	uint32_t* out32;    // kGatherTable: out32[o] = table[id], 0xFFFFFFFF when the k-mer is absent
+	uint32_t n_colors, color;
+};
+template <int MODE> constexpr bool mode_wants_slot() { return MODE == kLookupIds || MODE == kGatherTable; }
+template <int MODE> constexpr bool mode_wants_id() { return MODE != kLookupCount && MODE != kEmitPairs; }
+
+template <int MODE>
+__device__ __forceinline__ void emit(const Sink& K, int64_t id, uint64_t o) {
+	if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(K.ids + o), (long long)id);
+	else if (MODE == kConsumeCount) { if (id >= 0) atomicAdd(K.table + id, 1u); }
+	else if (MODE == kConsumeColor) {
+		if (id >= 0) { const uint64_t bit = (uint64_t)id * K.n_colors + K.color; atomicOr(K.table + (bit >> 5), 1u << (bit & 31)); }
+	} else if (MODE == kGatherTable) __stcs(K.out32 + o, id >= 0 ? __ldg(K.table + id) : 0xFFFFFFFFu);
+}
 
 // EAGER = BBHash levels probed in lock step before a k-mer is parked (kLevels: never park)
 template <int MODE, bool SMALL, int EAGER>
@@ -281,12 +302,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
                                                        const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                        const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
                                                        uint64_t strip_lo, uint64_t strip_hi, bool aligned16,
-                                                       int64_t* __restrict__ out_ids, uint64_t* __restrict__ ctr) {
+                                                       Sink K, uint64_t* __restrict__ ctr) {
+	constexpr bool kSlot = mode_wants_slot<MODE>(), kId = mode_wants_id<MODE>();
 	__shared__ uint32_t s_pack[kWarps][kStripWords];
 	__shared__ uint32_t s_bad[kWarps][kStripWords];
 	__shared__ uint32_t s_keys[kWarps][kKeySlots];   // key of position q at kidx(q)
 	__shared__ uint64_t s_run_T[kWarps][kMaxRuns];   // where the run's first k-mer matched (absolute base position)
-	__shared__ uint64_t s_run_o[MODE == kLookupIds ? kWarps : 1][kMaxRuns];  // output slot of the run's first k-mer
+	__shared__ uint64_t s_run_o[kSlot ? kWarps : 1][kMaxRuns];  // output slot of the run's first k-mer
 	__shared__ uint32_t s_run_mn[kWarps][kMaxRuns];  // minimizer of the run
 	__shared__ uint16_t s_run_q[kWarps][kMaxRuns];   // strip position of the run's first k-mer
 	__shared__ uint16_t s_run_dmax[kWarps][kMaxRuns];// largest distance whose predicted window still starts inside the bucket
@@ -298,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 	uint32_t* pack = s_pack[wid];
 	uint32_t* keys = s_keys[wid];
 	uint8_t* runid = reinterpret_cast<uint8_t*>(s_runid8[wid]);
-	const uint32_t ow = MODE == kLookupIds ? wid : 0;
+	const uint32_t ow = kSlot ? wid : 0;
 	const StripSmem S{pack, s_bad[wid], keys, s_run_q[wid], s_run_o[ow], s_runid8[wid]};
 	const uint32_t w = k - m + 1;
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
@@ -310,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
 		const uint64_t t0 = strip * kStrip;
 		__syncwarp();
-		const uint32_t n_runs = strip_front<MODE == kLookupIds>(S, lane, k, m, bases, read_off, read_end, kmer_off, n_reads, total_bases,
+		const uint32_t n_runs = strip_front<kSlot>(S, lane, k, m, bases, read_off, read_end, kmer_off, n_reads, total_bases,
 		                                                        reads_per_base, aligned16, t0, invalid);
 		uint32_t n_res = 0;
 		if (n_runs > (uint32_t)kMaxRuns) {
@@ -349,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 								left = false;
 								bool v;
 								int64_t idr = -1;
-								if (MODE == kLookupIds) {  // the launcher sends id queries here only when the table exists
+								if (kId) {  // the launcher sends id queries here only when the table exists
 									const uint32_t pid = __ldg(I.pos_id + Tp);
 									v = pid != 0xFFFFFFFFu;
 									if (v) idr = (int64_t)pid;
@@ -357,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 									v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
 								}
 								if (v) found++; else notfound++;
-								if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + d), (long long)idr);
+								if (kId) emit<MODE>(K, idr, kSlot ? s_run_o[ow][id] + d : 0);
 							}
 						}
 					}
@@ -381,9 +403,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 							keep = runid[q] == kTagOverflow || filter_maybe(I, f < rc ? f : rc);
 							if (!keep) {
 								notfound++;
-								if (MODE == kLookupIds) {
+								if (kSlot) {
 									const uint32_t id = runid[q];
-									__stcs(reinterpret_cast<long long*>(out_ids + s_run_o[ow][id] + (q - s_run_q[wid][id])), -1ll);
+									emit<MODE>(K, -1, s_run_o[ow][id] + (q - s_run_q[wid][id]));
 								}
 							}
 						}
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 						mn = mini_from_key(window_min_slow(keys, q, w));
 						if (phase == 0) s_run_mn[wid][id] = mn;
 					}
-					if (MODE == kLookupIds) {
+					if (kSlot) {
 						if (id != kTagOverflow) {
 							o = s_run_o[ow][id] + (q - s_run_q[wid][id]);
 						} else {
@@ -427,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 					const bool pass = !(phase == 0 && filter_anchors) || filter_maybe(I, x);
 					const int64_t idr = pass ? lookup_one<SMALL>(I, x, mn, &T) : -1;
 					if (idr >= 0) found++; else notfound++;
-					if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + o), (long long)idr);
+					if (kId) emit<MODE>(K, idr, o);
 					if (phase == 0) {
 						uint32_t flag = 0, dmax = 0;
 						if (idr >= 0) {
@@ -518,14 +540,14 @@ bool use_superkmer_kernel(bool want_ids, bool has_pos_id) {
 template <int MODE, bool SMALL>
 void launch_reads_sk(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
                      const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
-                     uint64_t strip_lo, uint64_t strip_hi, bool al, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream) {
+                     uint64_t strip_lo, uint64_t strip_hi, bool al, const Sink& sink, uint64_t* d_ctr, cudaStream_t stream) {
 	static const int per_sm = blocks_per_sm(k_reads_sk<MODE, SMALL>);
 	const uint64_t n_strips = strip_hi - strip_lo;
 	const uint64_t want = (n_strips + kWarps - 1) / kWarps;
 	const uint64_t cap = (uint64_t)sm_count() * per_sm;
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
 	k_reads_sk<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
-	                                                      strip_lo, strip_hi, al, d_ids, d_ctr);
+	                                                      strip_lo, strip_hi, al, sink, d_ctr);
 }
 
 template <int MODE, bool SMALL>
@@ -535,7 +557,7 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
                     cudaStream_t stream) {
 	if (MODE != kEmitPairs && v.valid && k - m + 1 >= 8 && use_superkmer_kernel(MODE == kLookupIds, v.pos_id != nullptr)) {
 		launch_reads_sk<MODE == kEmitPairs ? kLookupCount : MODE, SMALL>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
-		                                                                strip_lo, strip_hi, al, d_ids, d_ctr, stream);
+		                                                                strip_lo, strip_hi, al, Sink{d_ids, nullptr, nullptr, 0, 0}, d_ctr, stream);
 		return;
 	}
 	const int e = MODE == kEmitPairs ? 16 : eager_levels();
@@ -556,6 +578,28 @@ int launch_window_valid(const DevIndexView& I, uint64_t n_buckets, uint64_t tota
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
 	if (I.small) k_window_valid<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks);
 	else k_window_valid<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks);
+	g_launches++;
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) g_last_cuda_error = cudaGetErrorString(e);
+	return check(e);
+}
+
+int launch_reads_sink(const DevIndexView& I, int kind, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
+                      uint64_t n_reads, uint64_t total_bases, uint32_t* d_table, uint32_t n_colors, uint32_t color, uint32_t* d_out32,
+                      uint64_t* d_ctr, cudaStream_t stream) {
+	if (n_reads == 0 || total_bases == 0) return 0;
+	const uint64_t strip_hi = (total_bases + kStrip - 1) / kStrip;
+	const bool al = (reinterpret_cast<uintptr_t>(d_bases) & 15) == 0;
+	const Sink sink{nullptr, d_table, d_out32, n_colors, color};
+#define BL_SINK(MODE)                                                                                                              \
+	do {                                                                                                                            \
+		if (I.small) launch_reads_sk<MODE, true>(I, I.k, I.m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, 0, strip_hi, al, sink, d_ctr, stream); \
+		else launch_reads_sk<MODE, false>(I, I.k, I.m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, 0, strip_hi, al, sink, d_ctr, stream);        \
+	} while (0)
+	if (kind == 0) BL_SINK(kConsumeCount);
+	else if (kind == 1) BL_SINK(kConsumeColor);
+	else BL_SINK(kGatherTable);
+#undef BL_SINK
 	g_launches++;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) g_last_cuda_error = cudaGetErrorString(e);

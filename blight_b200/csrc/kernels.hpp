@@ -35,6 +35,13 @@ int launch_reads(const DevIndexView* I, uint32_t k, uint32_t m, const char* d_ba
                  uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream, uint64_t pos_begin = 0,
                  uint64_t pos_end = ~0ull);
 
+// The super-k-mer read kernel with an id consumer fused behind the lookup (needs I.pos_id and k - m + 1 >= 8):
+// kind 0: d_table[id] += 1; kind 1: bit id * n_colors + color of d_table set; kind 2: d_out32[d_kmer_off[r] + pos] = d_table[id]
+// (0xFFFFFFFF when absent). Counters are accumulated into d_ctr as in launch_reads.
+int launch_reads_sink(const DevIndexView& I, int kind, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
+                      uint64_t n_reads, uint64_t total_bases, uint32_t* d_table, uint32_t n_colors, uint32_t color, uint32_t* d_out32,
+                      uint64_t* d_ctr, cudaStream_t stream);
+
 // Start positions are handled in strips of this many bases; pos_begin of a partial launch must be a multiple of it.
 constexpr uint64_t kReadsStrip = 256;
 

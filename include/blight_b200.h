@@ -122,6 +122,21 @@ int blight_query_reads(const blight_index* idx, const char* d_bases, const uint6
                        const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, uint64_t total_kmers,
                        int64_t* d_ids, uint64_t* d_ctr, void* stream);
 
+/* ---- id consumers fused behind the lookup: what the reference's applications do with the ids of
+ * query_sequence_hash, done on the GPU so that ids never leave it. Need the position->id table (N < 2^32-1). ------- */
+#define BLIGHT_CONSUME_COUNT 0 /* d_table[id] += 1 (uint32): `abundance[kmer_ids[i]]++`, Abundance_De_Bruijn_graph_snippet.cpp:132-142
+                                  (the snippet's uint8 counter is this value mod 256) */
+#define BLIGHT_CONSUME_COLOR 1 /* bit id * n_colors + color of d_table set: `color[kmer_ids[i]*color_number+i_file]=true`,
+                                  Colored_De_Bruijn_graph_snippet.cpp:131-141 (vector<bool> bit order: bit j of word j/32) */
+int blight_consume_reads(const blight_index* idx, const char* d_bases, const uint64_t* d_read_off, uint64_t n_reads,
+                         uint64_t total_bases, int kind, uint32_t* d_table, uint32_t n_colors, uint32_t color, uint64_t* d_ctr,
+                         void* stream);
+/* The query side of the same applications (…snippet.cpp:176-192): d_out[d_kmer_off[r] + pos] = d_table[id] for every
+ * k-mer of every read, 0xFFFFFFFF for k-mers the index does not hold. */
+int blight_gather_reads(const blight_index* idx, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
+                        uint64_t n_reads, uint64_t total_bases, const uint32_t* d_table, uint32_t* d_out, uint64_t* d_ctr,
+                        void* stream);
+
 /* ---- host-buffer entry points (end to end: H2D, kernels, D2H inside the call) ------------------------- */
 
 /* kmer_Set_Light::file_query on a text buffer holding 2-line FASTA records (blight.cpp:746-799): same record

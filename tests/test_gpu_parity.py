@@ -230,6 +230,39 @@ def test_host_batch_in_many_chunks(tmp_path, torch_cuda, monkeypatch):
     assert (int(c3[0]), int(c3[1])) == (int(wctr[0]), int(wctr[1]))
 
 
+def test_file_query_streams_the_file(tmp_path, torch_cuda, monkeypatch):
+    """file_query(path): the streaming reader (chunks, carried partial records, plain and gzip, last line without a
+    newline, the reference's pairing quirks) gives the counters of the in-memory path and of the oracle."""
+    import gzip
+    g, ub, uo, rb, ro = common.synthetic(400_000, 6000, seed=55, sub_rate=0.02)
+    flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=9, n=7, s=0, b=6, threads=0)
+    port = common.cport_of(flat, tmp_path)
+    idx = flat.upload(0)
+    want, wctr = port.query_reads(rb, ro)
+    text = synth.fasta_bytes(rb, ro)
+    quirks = b"hdr-without-gt\n" + rb[:300].tobytes() + b"\n\n" + b"SWALLOWED\n" + b">x\n\n" + b">y\n" + rb[300:450].tobytes()  # no trailing newline
+    ref_q = idx.query_fasta_host(quirks)
+    plain, gz = tmp_path / "reads.fa", tmp_path / "reads.fa.gz"
+    plain.write_bytes(text + quirks)
+    with gzip.open(gz, "wb") as f:
+        f.write(text + quirks)
+    expect = [int(wctr[0]) + int(ref_q[0]), int(wctr[1]) + int(ref_q[1])]
+    for kb in ("1", "5", "300", "0"):
+        monkeypatch.setenv("BLIGHT_STREAM_CHUNK_KB", kb)
+        for path in (plain, gz):
+            c = idx.query_file_host(str(path))
+            assert [int(c[0]), int(c[1])] == expect, (kb, path)
+    monkeypatch.setenv("BLIGHT_FILE_QUERY", "whole")
+    c = idx.query_file_host(str(plain))
+    assert [int(c[0]), int(c[1])] == expect
+    monkeypatch.delenv("BLIGHT_FILE_QUERY")
+    empty = tmp_path / "empty.fa"
+    empty.write_bytes(b"")
+    assert int(idx.query_file_host(str(empty)).sum()) == 0
+    with pytest.raises(api.BlightError):
+        idx.query_file_host(str(tmp_path / "missing.fa"))
+
+
 def test_large_scale_properties(torch_cuda):
     """5 Mbp index / 1.2 M reads (beyond what the oracle checks in seconds): size-independent properties —
     self-query ids are a bijection on [0, N); a k-mer and its reverse complement get the same id; queries are
