@@ -55,3 +55,37 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".hpp", ".cuh", ".h")) or f == "Makefile":
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)
+
+
+CLI = os.path.join(ROOT, "blight_b200", "lib", "bench_blight_b200")
+
+
+def test_cli_usage_and_no_device(tmp_path):
+    """The C++ drop-in (kmer_set_light.hpp behind the reference's bench_blight.cpp option set): usage text without
+    arguments; without a GPU the run must fail loudly, never fall back to the CPU."""
+    import subprocess
+    import torch
+    from tests.golden import fixtures
+    assert os.path.exists(CLI), "build the cli target (python -c 'import __graft_entry__ as g; g.build()')"
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 0 and "Mandatory arguments" in r.stdout and "-b bit saved" in r.stdout
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    fa = tmp_path / "lambda.fa"
+    fa.write_bytes(fixtures.lambda_fasta())
+    r = subprocess.run([CLI, "-g", str(fa), "-k", "31", "-m", "7", "-n", "5", "-s", "3", "-b", "6"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and "Good kmer" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_lambda_self_query(tmp_path):
+    """bench_blight -g lambda_virus.unitigs.fa -k 31 -m 7 -n 5 -s 3 -b 6 (BASELINE configs[0]) through the C++ class:
+    Kmer in graph 48,462 / Good kmer 48,462 / Erroneous 0 / Query performed 48,462."""
+    import subprocess
+    from tests.golden import fixtures
+    fa = tmp_path / "lambda.fa"
+    fa.write_bytes(fixtures.lambda_fasta())
+    r = subprocess.run([CLI, "-g", str(fa), "-k", "31", "-m", "7", "-n", "5", "-s", "3", "-b", "6", "-t", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for line in ("Kmer in graph: 48462", "Super Kmer in graph: 3708", "Good kmer: 48462", "Erroneous kmers: 0", "Query performed: 48462"):
+        assert line in r.stdout, (line, r.stdout)
