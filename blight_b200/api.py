@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libblight_b200.so")
+LIB_PATH = os.environ.get("BLIGHT_B200_LIB") or os.path.join(_HERE, "lib", "libblight_b200.so")  # the override is for kernel experiments
 
 OK = 0
 ERR_INVALID_ARG, ERR_IO, ERR_INVALID_BASE, ERR_CUDA, ERR_NO_DEVICE, ERR_FORMAT, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7

@@ -374,8 +374,10 @@ int run_host_reads(const blight_index* idx, const char* text, uint64_t len, cons
 	CU(cudaEventRecord(static_cast<cudaEvent_t>(idx->ev_ws), st));  // the copy must not overtake the previous call's kernels
 	CU(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(idx->ev_ws), 0));
 	uint64_t copied = 0;
-	for (uint64_t c0 = 0; c0 < len; c0 += chunk) {
-		const uint64_t c1 = std::min(len, c0 + chunk);
+	// the first chunks are small (4 MB, doubling up to `chunk`): the first kernel starts after 0.1 ms of copy instead of 1.2 ms
+	uint64_t step = std::min<uint64_t>(chunk, 4ull << 20);
+	for (uint64_t c0 = 0; c0 < len;) {
+		const uint64_t c1 = std::min(len, c0 + step);
 		const uint64_t upto = std::min(len, c1 + halo);
 		if (upto > copied) {
 			CU(cudaMemcpyAsync(static_cast<char*>(d_text) + copied, text + copied, upto - copied, cudaMemcpyHostToDevice, cs));
@@ -387,6 +389,8 @@ int run_host_reads(const blight_index* idx, const char* text, uint64_t len, cons
 		                  static_cast<const uint64_t*>(end ? d_end : nullptr), static_cast<const uint64_t*>(d_koff), n, len, nullptr,
 		                  nullptr, static_cast<int64_t*>(d_ids), static_cast<uint64_t*>(d_ctr), st, c0, c1);
 		if (rc != BL_OK) return fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+		c0 = c1;
+		step = std::min<uint64_t>(chunk, step * 2);
 	}
 	if (ids_out && total_kmers) CU(cudaMemcpyAsync(ids_out, d_ids, total_kmers * 8, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(ctr, d_ctr, BLIGHT_N_CTR * 8, cudaMemcpyDeviceToHost, st));

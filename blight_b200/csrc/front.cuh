@@ -100,6 +100,62 @@ __device__ __noinline__ uint32_t window_min_slow(const uint32_t* keys, uint32_t 
 	return best;
 }
 
+// the 64 bases starting at strip position q, as four packed words (first base in the high bits of .x)
+__device__ __forceinline__ uint4 strip_bases64(const uint32_t* pack, uint32_t q) {
+	const uint32_t wi = q >> 4, s = 2u * (q & 15);
+	uint32_t v[5];
+	#pragma unroll
+	for (int i = 0; i < 5; i++) v[i] = (wi + i < (uint32_t)kStripWords) ? pack[wi + i] : 0u;
+	return make_uint4(__funnelshift_l(v[1], v[0], s), __funnelshift_l(v[2], v[1], s), __funnelshift_l(v[3], v[2], s), __funnelshift_l(v[4], v[3], s));
+}
+
+// the 64 bases of the packed bucket sequences starting at base P (five word loads, one or two sectors)
+__device__ __forceinline__ uint4 seq_bases64(const uint32_t* __restrict__ seq, uint64_t P) {
+	const uint32_t* p = seq + (P >> 4);
+	const uint32_t s = 2u * (uint32_t)(P & 15);
+	const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+	return make_uint4(__funnelshift_l(b, a, s), __funnelshift_l(c, b, s), __funnelshift_l(d, c, s), __funnelshift_l(e, d, s));
+}
+
+// reverse complement of a 64-base block (base j of the result = complement of base 63 - j)
+__device__ __forceinline__ uint4 rc_bases64(uint4 r) {
+	auto rc16 = [](uint32_t w) {
+		uint32_t t = __brev(w ^ 0xAAAAAAAAu);
+		return ((t & 0x55555555u) << 1) | ((t >> 1) & 0x55555555u);
+	};
+	return make_uint4(rc16(r.w), rc16(r.z), rc16(r.y), rc16(r.x));
+}
+
+// 64 bases shifted towards the front by `n` bases (n <= 64), zero filled
+__device__ __forceinline__ uint4 shl_bases64(uint4 r, uint32_t n) {
+	uint64_t hi = ((uint64_t)r.x << 32) | r.y, lo = ((uint64_t)r.z << 32) | r.w;
+	const uint32_t sh = 2 * n;
+	if (sh >= 64) { hi = sh >= 128 ? 0 : lo << (sh - 64); lo = 0; }
+	else if (sh) { hi = (hi << sh) | (lo >> (64 - sh)); lo <<= sh; }
+	return make_uint4((uint32_t)(hi >> 32), (uint32_t)hi, (uint32_t)(lo >> 32), (uint32_t)lo);
+}
+
+// For two 64-base blocks: bit 63 - j of the result is set iff the k bases starting at base j differ somewhere
+// (bases past the block count as equal). One lane compares a whole super-k-mer against the index text this way.
+__device__ __forceinline__ uint64_t mismatch_windows64(uint4 a, uint4 b, uint32_t k) {
+	auto comp = [](uint32_t d) {  // 16 bases, 2 bits each -> 16 bits, 1 = the base differs; first base -> bit 15
+		uint32_t x = (d | (d >> 1)) & 0x55555555u;
+		x = (x | (x >> 1)) & 0x33333333u;
+		x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+		x = (x | (x >> 4)) & 0x00FF00FFu;
+		return (x | (x >> 8)) & 0xFFFFu;
+	};
+	const uint64_t M = ((uint64_t)comp(a.x ^ b.x) << 48) | ((uint64_t)comp(a.y ^ b.y) << 32) | ((uint64_t)comp(a.z ^ b.z) << 16) | comp(a.w ^ b.w);
+	uint64_t A = M;  // OR over a window of k bases, by doubling: bit p collects bits p, p-1, .., p-k+1
+	#pragma unroll 1
+	for (uint32_t win = 1; win < k;) {
+		const uint32_t sh = min(win, k - win);
+		A |= A << sh;
+		win += sh;
+	}
+	return A;
+}
+
 // Shared-memory slice of one warp.
 struct StripSmem {
 	uint32_t* pack;    // [kStripWords]  2-bit codes, 16 per word, first base in the high bits

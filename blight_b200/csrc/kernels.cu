@@ -297,8 +297,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 // 32 KB instruction cache, warps sit at unrelated program counters (the v6 profile lost 20 % of its issue slots to
 // instruction fetch).
 // Answers are identical to k_reads: a window that equals the query decides "found" exactly as the reference does.
+// resident CTAs per SM the super-k-mer kernel is compiled for: 4 (64 registers). Measured: 5 (48 registers, 64 bytes of
+// spills) 44.1 ms vs 41.3 ms per 1.2 G k-mers in counting mode.
+#ifndef BLIGHT_SK_BLOCKS
+#define BLIGHT_SK_BLOCKS 4
+#endif
+
 template <int MODE, bool SMALL>
-__global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
+__global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                        const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                        const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
                                                        uint64_t strip_lo, uint64_t strip_hi, bool aligned16,
@@ -315,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 	__shared__ uint8_t s_run_flag[kWarps][kMaxRuns]; // bit0: first k-mer found, bit1: text and read on the same strand
 	__shared__ uint64_t s_runid8[kWarps][kStrip / 8];// run of every strip position, one byte each
 	__shared__ uint8_t s_resid[kWarps][kStrip];      // positions left for C4
+	__shared__ uint64_t s_run_okv[kWarps][kMaxRuns]; // C3a: which k-mers of the run match their predicted window (low half) and those windows' valid bits
 
 	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	uint32_t* pack = s_pack[wid];
@@ -351,36 +358,61 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads_sk(DevIndexView I, uint32
 		#pragma unroll 1
 		for (int phase = 0; phase < 2; phase++) {
 			if (phase == 1) {
-				// C3. every other k-mer of a run: one window, next to where the first one matched
+				// C3a. one lane per run: the run's text against the index text next to where its first k-mer matched, all of the
+				// run's windows at once (64 bases each side; 2-bit XOR -> per-base mismatch bits -> OR over k consecutive bases).
+				// Bit d of the low half: k-mer d of the run equals the window at T +- d; of the high half: that window's valid bit.
+				#pragma unroll 1
+				for (uint32_t base = 0; base < n_anch; base += 32) {
+					const uint32_t id = base + lane;
+					if (id < n_anch) {
+						uint64_t okv = 0;
+						const uint32_t flag = s_run_flag[wid][id];
+						const uint32_t cnt = min(31u, (uint32_t)s_run_dmax[wid][id]);  // k-mers 1..cnt have their window inside the bucket
+						if ((flag & 1) && cnt) {
+							const bool same = flag & 2;
+							const uint64_t Ta = s_run_T[wid][id];
+							const uint64_t S0 = same ? Ta : Ta - cnt;  // first base of the index text that is compared
+							uint4 R = strip_bases64(pack, s_run_q[wid][id]);
+							if (!same) R = shl_bases64(rc_bases64(R), 64 - (cnt + k));  // the cnt + k bases of the run, reverse complemented
+							const uint64_t A = mismatch_windows64(R, seq_bases64(I.seq, S0), k);
+							// same strand: window j = k-mer j; opposite strand: window j = k-mer cnt - j
+							uint32_t ok = same ? __brev((uint32_t)(~A >> 32)) : (uint32_t)(~A >> (63 - cnt));
+							ok &= cnt == 31 ? 0xFFFFFFFEu : ((2u << cnt) - 2u);
+							uint32_t v = 0;
+							if (!kId) {
+								const uint32_t* vp = I.valid + (S0 >> 5);
+								const uint32_t u = __funnelshift_r(__ldg(vp), __ldg(vp + 1), (uint32_t)(S0 & 31));  // bit j = valid[S0 + j]
+								v = same ? u : (__brev(u) >> (31 - cnt));
+							}
+							okv = ok | ((uint64_t)v << 32);
+						}
+						s_run_okv[wid][id] = okv;
+					}
+				}
+				__syncwarp();
+				// C3b. every position: answered by its run's masks, or left for the lookup
 				#pragma unroll 1
 				for (int it = 0; it < kPerLane; it++) {
 					const uint32_t q = it * 32 + lane;
 					const uint32_t id = runid[q];
 					bool left = false;
 					if (id < (uint32_t)kMaxRuns && q != s_run_q[wid][id]) {
-						left = true;
-						const uint32_t flag = s_run_flag[wid][id];
 						const uint32_t d = q - s_run_q[wid][id];
-						if ((flag & 1) && d <= s_run_dmax[wid][id]) {
-							const bool same = flag & 2;
-							const uint64_t Ta = s_run_T[wid][id];
-							const uint64_t Tp = same ? Ta + d : Ta - d;
-							const uint64_t f = strip_kmer(pack, q, k), rc = rc64(f, k);
-							if (window_at(I.seq, Tp, k) == (same ? f : rc)) {
-								// the query equals this window, so the reference's answer is the window's own
-								left = false;
-								bool v;
-								int64_t idr = -1;
-								if (kId) {  // the launcher sends id queries here only when the table exists
-									const uint32_t pid = __ldg(I.pos_id + Tp);
-									v = pid != 0xFFFFFFFFu;
-									if (v) idr = (int64_t)pid;
-								} else {
-									v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
-								}
-								if (v) found++; else notfound++;
-								if (kId) emit<MODE>(K, idr, kSlot ? s_run_o[ow][id] + d : 0);
+						const uint64_t okv = s_run_okv[wid][id];
+						if (d < 32 && ((okv >> d) & 1)) {
+							// the query equals this window, so the reference's answer is the window's own
+							bool v;
+							if (kId) {  // the launcher sends id queries here only when the table exists
+								const uint64_t Ta = s_run_T[wid][id];
+								const uint32_t pid = __ldg(I.pos_id + ((s_run_flag[wid][id] & 2) ? Ta + d : Ta - d));
+								v = pid != 0xFFFFFFFFu;
+								emit<MODE>(K, v ? (int64_t)pid : -1, kSlot ? s_run_o[ow][id] + d : 0);
+							} else {
+								v = (okv >> (32 + d)) & 1;
 							}
+							if (v) found++; else notfound++;
+						} else {
+							left = true;
 						}
 					}
 					const uint32_t lm = __ballot_sync(0xffffffffu, left);

@@ -70,15 +70,6 @@ __device__ __forceinline__ uint32_t owner_of(const Route& R, uint32_t mini) {
 	return o;
 }
 
-// the 64 bases starting at strip position q, as four packed words
-__device__ __forceinline__ uint4 strip_bases64(const uint32_t* pack, uint32_t q) {
-	const uint32_t wi = q >> 4, s = 2u * (q & 15);
-	uint32_t v[5];
-	#pragma unroll
-	for (int i = 0; i < 5; i++) v[i] = (wi + i < (uint32_t)kStripWords) ? pack[wi + i] : 0u;
-	return make_uint4(__funnelshift_l(v[1], v[0], s), __funnelshift_l(v[2], v[1], s), __funnelshift_l(v[3], v[2], s), __funnelshift_l(v[4], v[3], s));
-}
-
 template <bool WANT_O>
 __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                              const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
