@@ -20,7 +20,6 @@ constexpr int kPerLane = kStrip / 32;
 constexpr int kMaxW = 32;                            // k - m + 1 <= 31
 constexpr int kStripWords = (kStrip + 32) / 16 + 2;  // packed words per strip (+halo k-1 <= 30, +1 for the funnel)
 constexpr int kStripKeys = kStrip + kMaxW;
-constexpr int kQueue = 64;                           // straggler slots per warp (at most 31 waiting + 32 new)
 static_assert(kStripWords <= 32, "one lane packs one word");
 
 // first read r in [0, n_reads) with off[r+1] > p, i.e. the read containing base position p (or the gap before it).

@@ -98,8 +98,7 @@ __device__ __forceinline__ void emit(const Sink& K, int64_t id, uint64_t o) {
 	} else if (MODE == kGatherTable) __stcs(K.out32 + o, id >= 0 ? __ldg(K.table + id) : 0xFFFFFFFFu);
 }
 
-// EAGER = BBHash levels probed in lock step before a k-mer is parked (kLevels: never park)
-template <int MODE, bool SMALL, int EAGER>
+template <int MODE, bool SMALL>
 __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                     const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                     const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
@@ -109,14 +108,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 	__shared__ uint32_t s_pack[kWarps][kStripWords];  // 2-bit codes, 16 per word, first base in the high bits
 	__shared__ uint32_t s_bad[kWarps][kStripWords];   // 1 bit per base (bit 15-j of word i = base 16i+j): not ACGTacgt
 	__shared__ uint32_t s_keys[kWarps][kStripKeys];   // ordering key of the m-mer starting at each strip position
-	// Straggler queue of the warp: k-mers that no bit accommodated in BBHash levels 0..EAGER-1 (~22 % of a read
-	// batch). A warp would otherwise iterate the level loop to its slowest lane with a handful of lanes active; such
-	// k-mers are parked here with their hasher state and finished 32 at a time with every lane busy.
-	constexpr bool kParks = MODE != kEmitPairs && EAGER < kLevels;
-	__shared__ uint64_t q_x[kParks ? kWarps : 1][kParks ? kQueue : 1], q_s0[kParks ? kWarps : 1][kParks ? kQueue : 1];
-	__shared__ uint64_t q_s1[kParks ? kWarps : 1][kParks ? kQueue : 1], q_off[kParks ? kWarps : 1][kParks ? kQueue : 1];
-	__shared__ uint64_t q_o[kParks && MODE == kLookupIds ? kWarps : 1][kParks ? kQueue : 1];
-	__shared__ uint32_t q_mn[kParks ? kWarps : 1][kParks ? kQueue : 1];
 
 	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	uint32_t* pack = s_pack[wid];
@@ -124,145 +115,74 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 	uint32_t* keys = s_keys[wid];
 	const uint32_t w = k - m + 1;
 	const uint32_t mmask = (1u << (2 * m)) - 1u;
-	const uint64_t n_strips = strip_hi;  // this launch handles strips [strip_lo, strip_hi) of the buffer
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
 	const double reads_per_base = (double)n_reads / (double)total_bases;
 	uint32_t found = 0, notfound = 0, invalid = 0;
-	uint32_t q_head = 0, q_count = 0;  // warp-uniform
-	const uint32_t qw = kParks ? wid : 0;
 
-	uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid;
-	uint64_t t0 = 0, r = 0;
-	uint32_t n_pos = 0;
-	int it = 0;
-	for (;;) {
-		const bool flush = strip >= n_strips;  // one extra turn after the last strip empties the queue
-		if (!flush && it == 0) {
-			t0 = strip * kStrip;
-			n_pos = (uint32_t)min((uint64_t)kStrip, total_bases - t0);                        // positions owned by this strip
-			const uint32_t n_load = (uint32_t)min((uint64_t)(kStrip + 32), total_bases - t0);  // owned + halo (k-1 <= 30)
-			__syncwarp();
-			// A. pack: lane i converts bases [16i, 16i+16) of the strip
-			if (lane < kStripWords) {
-				const uint32_t b0 = lane * 16;
-				uint32_t word = 0, badw = 0;
-				if (b0 < n_load) {
-					unsigned char ch[16];
-					if (aligned16 && b0 + 16 <= n_load) {
-						const uint4 v = __ldcs(reinterpret_cast<const uint4*>(bases + t0 + b0));  // t0 % 256 == 0
-						*reinterpret_cast<uint4*>(ch) = v;
-					} else {
-						#pragma unroll
-						for (int j = 0; j < 16; j++) ch[j] = (b0 + j < n_load) ? (unsigned char)bases[t0 + b0 + j] : (unsigned char)'A';
-					}
-					#pragma unroll
-					for (int j = 0; j < 16; j++) {
-						const uint32_t c = nuc_code(ch[j]);
-						badw = (badw << 1) | (c >> 2);
-						word = (word << 2) | (c & 3u);
-					}
+	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
+		const uint64_t t0 = strip * kStrip;
+		const uint32_t n_pos = (uint32_t)min((uint64_t)kStrip, total_bases - t0);                        // positions owned by this strip
+		const uint32_t n_load = (uint32_t)min((uint64_t)(kStrip + 32), total_bases - t0);  // owned + halo (k-1 <= 30)
+		__syncwarp();
+		// A. pack: lane i converts bases [16i, 16i+16) of the strip
+		if (lane < kStripWords) {
+			const uint32_t b0 = lane * 16;
+			uint32_t word = 0, badw = 0;
+			if (b0 < n_load) {
+				const uint4 v = (aligned16 && b0 + 16 <= n_load) ? __ldcs(reinterpret_cast<const uint4*>(bases + t0 + b0))  // t0 % 256 == 0
+				                                                  : load16_slow(bases + t0 + b0, n_load - b0);
+				unsigned char ch[16];
+				*reinterpret_cast<uint4*>(ch) = v;
+				#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const uint32_t c = nuc_code(ch[j]);
+					badw = (badw << 1) | (c >> 2);
+					word = (word << 2) | (c & 3u);
 				}
-				pack[lane] = word;
-				bad[lane] = badw;
 			}
-			// read containing the first position of the strip (lane 0 searches, everybody starts from there)
-			if (lane == 0) r = find_read(read_off, n_reads, reads_per_base, t0);
-			r = __shfl_sync(0xffffffffu, r, 0);
-			__syncwarp();
-			// B. m-mer keys
-			for (uint32_t q = lane; q < n_pos + w - 1; q += 32) {
-				const uint32_t wi = q >> 4, s = 2u * (q & 15);
-				const uint32_t v = __funnelshift_l(pack[wi + 1], pack[wi], s) >> (32 - 2 * m);
-				keys[q] = mini_key(parity_canon(v & mmask, m));
-			}
-			__syncwarp();
+			pack[lane] = word;
+			bad[lane] = badw;
 		}
-
+		// read containing the first position of the strip (lane 0 searches, everybody starts from there)
+		uint64_t r = 0;
+		if (lane == 0) r = find_read(read_off, n_reads, reads_per_base, t0);
+		r = __shfl_sync(0xffffffffu, r, 0);
+		__syncwarp();
+		// B. m-mer keys
+		for (uint32_t q = lane; q < n_pos + w - 1; q += 32) {
+			const uint32_t wi = q >> 4, s = 2u * (q & 15);
+			const uint32_t v = __funnelshift_l(pack[wi + 1], pack[wi], s) >> (32 - 2 * m);
+			keys[q] = mini_key(parity_canon(v & mmask, m));
+		}
+		__syncwarp();
 		// C. one k-mer per lane: adjacent lanes, adjacent positions
-		bool have = false;
-		uint64_t hx = 0, ho = 0;
-		uint32_t hmn = 0;
-		const uint32_t q = it * 32 + lane;
-		if (!flush && q < n_pos) {
+		#pragma unroll 1
+		for (uint32_t q = lane; q < n_pos; q += 32) {
 			const uint64_t p = t0 + q;
 			while (r + 1 < n_reads && __ldg(read_off + r + 1) <= p) r++;  // positions only grow: gallop forward
 			const uint64_t rbeg = __ldg(read_off + r), rend = read_end ? __ldg(read_end + r) : __ldg(read_off + r + 1);
-			if (p >= rbeg && p + k <= rend) {  // else no k-mer starts here (tail of a read, a gap, a read shorter than k)
-				const uint32_t wi = q >> 4, s = 2u * (q & 15);
-				// nuc2int rejects any byte outside ACGTacgt (kmer.h:56-69); only bases of queried k-mers are ever looked at
-				const uint64_t bb = ((uint64_t)bad[wi] << 32) | ((uint64_t)bad[wi + 1] << 16) | bad[wi + 2];
-				if ((bb >> (48 - (q & 15) - k)) & ((1ull << k) - 1)) {
-					invalid++;
-				} else {
-					uint32_t best = keys[q];
-					for (uint32_t j = 1; j < w; j++) best = min(best, keys[q + j]);
-					const uint32_t a = pack[wi], b = pack[wi + 1], c = pack[wi + 2];
-					const uint64_t top = ((uint64_t)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s);
-					const uint64_t fwd = top >> (64 - 2 * k);
-					const uint64_t rc = rc64(fwd, k);
-					hx = fwd < rc ? fwd : rc;
-					hmn = mini_from_key(best);
-					if (MODE != kLookupCount) ho = __ldg(kmer_off + r) + (p - rbeg);
-					have = true;
-				}
+			if (!(p >= rbeg && p + k <= rend)) continue;  // no k-mer starts here (tail of a read, a gap, a read shorter than k)
+			const uint32_t wi = q >> 4, s = 2u * (q & 15);
+			// nuc2int rejects any byte outside ACGTacgt (kmer.h:56-69); only bases of queried k-mers are ever looked at
+			const uint64_t bb = ((uint64_t)bad[wi] << 32) | ((uint64_t)bad[wi + 1] << 16) | bad[wi + 2];
+			if ((bb >> (48 - (q & 15) - k)) & ((1ull << k) - 1)) { invalid++; continue; }
+			uint32_t best = keys[q];
+			for (uint32_t j = 1; j < w; j++) best = min(best, keys[q + j]);
+			const uint32_t a = pack[wi], b = pack[wi + 1], c = pack[wi + 2];
+			const uint64_t fwd = ((((uint64_t)__funnelshift_l(b, a, s)) << 32) | __funnelshift_l(c, b, s)) >> (64 - 2 * k);
+			const uint64_t rc = rc64(fwd, k);
+			const uint64_t x = fwd < rc ? fwd : rc;
+			const uint32_t mn = mini_from_key(best);
+			const uint64_t o = MODE != kLookupCount ? __ldg(kmer_off + r) + (p - rbeg) : 0;
+			if (MODE == kEmitPairs) {
+				__stcs(reinterpret_cast<unsigned long long*>(out_canon + o), (unsigned long long)x);
+				__stcs(out_mini + o, mn);
+			} else {
+				const int64_t id = lookup_one<SMALL>(I, x, mn);
+				if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + o), (long long)id);
+				if (id >= 0) found++; else notfound++;
 			}
 		}
-		if (MODE == kEmitPairs) {
-			if (have) {
-				__stcs(reinterpret_cast<unsigned long long*>(out_canon + ho), (unsigned long long)hx);
-				__stcs(out_mini + ho, hmn);
-			}
-		} else {
-			// the strip's k-mers: bucket, then levels 0..EAGER-1 in lock step
-			bool go = false, hit = false, park = false;
-			BucketRef B;
-			uint32_t sw[8];
-			uint32_t sr = 0;
-			uint64_t s0 = 0, s1 = 0, off = 0;
-			if (have) {
-				B = load_bucket(I, hmn);
-				if (B.bd.z == 0) {  // empty bucket (blight.cpp:719)
-					notfound++;
-					if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + ho), -1ll);
-				} else {
-					hit = probe_levels<SMALL>(B, hx, 0, EAGER, s0, s1, off, sw, sr);
-					go = hit || !kParks;
-					park = !hit && kParks;
-				}
-			}
-			const uint32_t pm = kParks ? __ballot_sync(0xffffffffu, park) : 0u;
-			if (kParks && park) {
-				const uint32_t slot = (q_head + q_count + __popc(pm & ((1u << lane) - 1u))) & (kQueue - 1);
-				q_x[qw][slot] = hx; q_s0[qw][slot] = s0; q_s1[qw][slot] = s1; q_off[qw][slot] = off; q_mn[qw][slot] = hmn;
-				if (MODE == kLookupIds) q_o[qw][slot] = ho;
-			}
-			q_count += __popc(pm);
-			__syncwarp();
-			// finish the eager hits, then whole warps of parked k-mers while there are enough of them
-			for (;;) {
-				if (go) {
-					const int64_t id = finish_lookup(I, B, hx, hit, sw, sr);
-					if (MODE == kLookupIds) __stcs(reinterpret_cast<long long*>(out_ids + ho), (long long)id);
-					if (id >= 0) found++; else notfound++;
-				}
-				if (!kParks || q_count < (flush ? 1u : 32u)) break;
-				const uint32_t take = q_count < 32 ? q_count : 32;
-				go = lane < take;
-				if (go) {
-					const uint32_t slot = (q_head + lane) & (kQueue - 1);
-					hx = q_x[qw][slot]; hmn = q_mn[qw][slot];
-					s0 = q_s0[qw][slot]; s1 = q_s1[qw][slot]; off = q_off[qw][slot];
-					if (MODE == kLookupIds) ho = q_o[qw][slot];
-					B = load_bucket(I, hmn);
-					hit = probe_levels<SMALL>(B, hx, EAGER, kLevels, s0, s1, off, sw, sr);
-				}
-				q_head = (q_head + take) & (kQueue - 1);
-				q_count -= take;
-				__syncwarp();
-			}
-		}
-		if (flush) break;
-		if (++it == kPerLane) { it = 0; strip += warp_stride; }
 	}
 
 	#pragma unroll
@@ -533,27 +453,18 @@ int blocks_per_sm(K kernel) {
 	return nb;
 }
 
-int eager_levels() {
-	static const int v = [] {
-		const char* e = getenv("BLIGHT_EAGER_LEVELS");  // tuning knob: 2, 3 or 16 (never park)
-		const int x = e ? atoi(e) : 16;
-		return (x == 2 || x == 3) ? x : 16;
-	}();
-	return v;
-}
-
-template <int MODE, bool SMALL, int EAGER>
-void launch_reads_e(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
-                    const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
-                    uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
-                    cudaStream_t stream) {
-	static const int per_sm = blocks_per_sm(k_reads<MODE, SMALL, EAGER>);
+template <int MODE, bool SMALL>
+void launch_reads_plain(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
+                        const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
+                        uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
+                        cudaStream_t stream) {
+	static const int per_sm = blocks_per_sm(k_reads<MODE, SMALL>);
 	const uint64_t n_strips = strip_hi - strip_lo;
 	const uint64_t want = (n_strips + kWarps - 1) / kWarps;
 	const uint64_t cap = (uint64_t)sm_count() * per_sm;  // persistent: one resident wave, warps stride over the strips
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
-	k_reads<MODE, SMALL, EAGER><<<grid, kThreads, 0, stream>>>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
-	                                                          strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr);
+	k_reads<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
+	                                                   strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr);
 }
 
 // Which read kernel serves a mode. Measured on B200 (100 M-k-mer index, b=6): counting mode 1.88e10 k-mers/s with the
@@ -592,10 +503,7 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
 		                                                                strip_lo, strip_hi, al, Sink{d_ids, nullptr, nullptr, 0, 0}, d_ctr, stream);
 		return;
 	}
-	const int e = MODE == kEmitPairs ? 16 : eager_levels();
-	if (e == 2) launch_reads_e<MODE, SMALL, 2>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
-	else if (e == 3) launch_reads_e<MODE, SMALL, 3>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
-	else launch_reads_e<MODE, SMALL, kLevels>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
+	launch_reads_plain<MODE, SMALL>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
 }
 
 }  // namespace

@@ -264,24 +264,6 @@ __device__ __forceinline__ int64_t finish_lookup(const DevIndexView& I, const Bu
 	return (int64_t)((uint64_t)rank + (((uint64_t)m1.y << 32) | m1.x));
 }
 
-// Identifier of a key for which the answer "found" is already established (see DevIndexView::valid): only the MPHF
-// rank is needed, no position read and no window scan.
-template <bool SMALL>
-__device__ __forceinline__ int64_t id_of_found(const DevIndexView& I, const BucketRef& B, uint64_t x) {
-	uint64_t s0 = 0, s1 = 0, off = 0;
-	uint32_t w[8];
-	uint32_t r = 0;
-	const bool hit = probe_levels<SMALL>(B, x, 0, kLevels, s0, s1, off, w, r);
-	const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(B.M) + 1);
-	uint32_t rank;
-	if (hit) rank = rank_in_sector(w, r);
-	else {
-		const uint4 m2 = __ldg(reinterpret_cast<const uint4*>(B.M) + 2);
-		if (!fallback_rank(I, m1, m2, x, rank)) return -1;  // cannot happen for a key the reference finds
-	}
-	return (int64_t)((uint64_t)rank + (((uint64_t)m1.y << 32) | m1.x));
-}
-
 // ---- the negative filter (device_index.hpp: `filter`) ----------------------------------------------------------------
 // block = hi32(h) scaled to the block count, bit i of the key = 5 bits of a second product, one per word of the block.
 __device__ __forceinline__ uint64_t filter_hash(uint64_t x) {
