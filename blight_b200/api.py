@@ -106,7 +106,7 @@ def lib() -> C.CDLL:
     L.blight_consume_reads.argtypes = [vp, vp, vp, u64, u64, C.c_int, vp, u32, u32, vp, vp]
     L.blight_gather_reads.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp]
     L.blight_part_dispatch.argtypes = [u32, u32, vp, vp, vp, u64, u64, u64, u64, C.POINTER(PartRoute), vp, vp, vp, vp]
-    L.blight_part_lookup.argtypes = [vp, u32, C.POINTER(vp), vp, C.POINTER(vp), u64, vp, vp]
+    L.blight_part_lookup.argtypes = [vp, u32, C.POINTER(vp), vp, C.POINTER(vp), u64, u64, vp, vp]
     L.blight_part_scatter.argtypes = [vp, u64, vp, vp, u64, u32, u64, vp, vp]
     L.blight_peer_alloc.argtypes = [u64, C.POINTER(vp), C.c_char_p]
     L.blight_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
@@ -392,13 +392,13 @@ def part_dispatch(k, m, bases, read_off, kmer_off, route: PartRoute, counts, ctr
                                       _stream_handle(stream)))
 
 
-def part_lookup(index: "DeviceIndex", regions: Sequence[int], counts, ret_ptrs: Optional[Sequence[int]], max_records: int, ctr, stream=None):
+def part_lookup(index: "DeviceIndex", regions: Sequence[int], counts, ret_ptrs: Optional[Sequence[int]], cap: int, kcap: int, ctr, stream=None):
     """Owner side: looks the received runs up and stores 32-bit ids into its return region at every source
     (ret_ptrs None = counting mode)."""
     world = len(regions)
     reg = (C.c_void_p * world)(*regions)
     retp = (C.c_void_p * world)(*ret_ptrs) if ret_ptrs is not None else None
-    _check(lib().blight_part_lookup(index._h, world, reg, _ptr(counts), retp, max_records, _ptr(ctr), _stream_handle(stream)))
+    _check(lib().blight_part_lookup(index._h, world, reg, _ptr(counts), retp, cap, kcap, _ptr(ctr), _stream_handle(stream)))
 
 
 def part_scatter(side_ptr: int, cap: int, counts, ret_ptr: int, kcap: int, world: int, max_records: int, ids, stream=None):

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 
 struct OwnerArgs {
 	uint32_t world, pad;
+	uint64_t cap, kcap;               // records per inbox region, ids per return region
 	const RunRec* region[kMaxRanks];  // records received from every source
 	uint32_t* ret[kMaxRanks];         // this owner's return region at every source (peer pointers), unused in counting mode
 };
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 	__shared__ uint16_t s_dmax[kWarps][32];
 	__shared__ uint16_t s_incl[kWarps][32];  // inclusive prefix of n: the ids of the warp's runs, flattened, live at [incl[r-1], incl[r])
 	__shared__ uint8_t s_flag[kWarps][32];
+	__shared__ uint64_t s_okv[kWarps][32];
 	__shared__ uint16_t s_res[kWarps][kResCap];                 // work list: flattened indices waiting for the whole lookup
 	__shared__ uint32_t s_ids[WANT_IDS ? kWarps : 1][kMaxIds];  // the warp's answers, in the order they travel back
 
@@ -250,7 +252,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 	if (threadIdx.x == 0) {
 		unsigned long long acc = 0;
 		for (uint32_t s = 0; s < A.world; s++) {
-			const unsigned long long c = counts[s] >> kKmerBits;
+			// a source that ran out of room dropped the records past `cap` (and raised its error flag: the batch is answered
+			// again through another path); never read past the region
+			const unsigned long long c = min(counts[s] >> kKmerBits, (unsigned long long)A.cap);
 			s_cnt[s] = c;
 			s_pref[s] = acc;
 			acc += (c + 31) / 32;
@@ -260,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 	__syncthreads();
 	const uint64_t n_chunks = s_pref[A.world];
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
+	const uint32_t mn_limit = 1u << (2 * I.m - 1);
 	uint32_t found = 0, notfound = 0;
 
 	for (uint64_t chunk = (uint64_t)blockIdx.x * kWarps + wid; chunk < n_chunks; chunk += warp_stride) {
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 			uint32_t* W = s_w[wid][lane];
 			W[0] = b.x; W[1] = b.y; W[2] = b.z; W[3] = b.w; W[4] = 0;
 			ko = h.x;
-			s_mn[wid][lane] = h.y;
+			s_mn[wid][lane] = h.y < mn_limit ? h.y : 0u;  // (a slot the source dropped holds an older record or zeros: stay in bounds)
 			n = min(h.z & 0xFFu, kMaxRecKmers);
 		}
 		uint32_t incl = n;
@@ -355,9 +360,39 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 				}
 			}
 			n_res = 0;
-			anchors = false;
 			__syncwarp();
-			// fill: every other k-mer of a run against the one window next to where the first one matched
+			if (anchors) {
+				// one lane per run: the run's text against the index text next to where its first k-mer matched, all of its windows
+				// at once (front.cuh: mismatch_windows64). Low half of okv: k-mer d equals the window at T +- d; high half: that
+				// window's valid bit.
+				uint64_t okv = 0;
+				if (lane < n_first) {
+					const uint32_t flag = s_flag[wid][lane];
+					const uint32_t cnt = min(31u, (uint32_t)s_dmax[wid][lane]);
+					if ((flag & 1) && cnt) {
+						const bool same = flag & 2;
+						const uint64_t Ta = s_T[wid][lane];
+						const uint64_t S0 = same ? Ta : Ta - cnt;
+						const uint32_t* W = s_w[wid][lane];
+						uint4 R = make_uint4(W[0], W[1], W[2], W[3]);
+						if (!same) R = shl_bases64(rc_bases64(R), 64 - (cnt + k));
+						const uint64_t Am = mismatch_windows64(R, seq_bases64(I.seq, S0), k);
+						uint32_t ok = same ? __brev((uint32_t)(~Am >> 32)) : (uint32_t)(~Am >> (63 - cnt));
+						ok &= cnt == 31 ? 0xFFFFFFFEu : ((2u << cnt) - 2u);
+						uint32_t v = 0;
+						if (!WANT_IDS) {
+							const uint32_t* vp = I.valid + (S0 >> 5);
+							const uint32_t u = __funnelshift_r(__ldg(vp), __ldg(vp + 1), (uint32_t)(S0 & 31));
+							v = same ? u : (__brev(u) >> (31 - cnt));
+						}
+						okv = ok | ((uint64_t)v << 32);
+					}
+				}
+				s_okv[wid][lane] = okv;
+				anchors = false;
+				__syncwarp();
+			}
+			// fill: every other k-mer of a run is answered by its run's masks, or joins the work list
 			#pragma unroll 1
 			while (base < n_ids && n_res + 32 <= (uint32_t)kResCap) {
 				const uint32_t i = base + lane;
@@ -366,25 +401,20 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 					const uint32_t run = run_of(s_incl[wid], i);
 					const uint32_t d = i - (run ? s_incl[wid][run - 1] : 0u);
 					if (d) {
-						left = true;
-						const uint32_t flag = s_flag[wid][run];
-						if ((flag & 1) && d <= s_dmax[wid][run]) {
-							const bool same = flag & 2;
-							const uint64_t Ta = s_T[wid][run];
-							const uint64_t Tp = same ? Ta + d : Ta - d;
-							const uint64_t f = rec_kmer(s_w[wid][run], d, k), rc = rc64(f, k);
-							if (window_at(I.seq, Tp, k) == (same ? f : rc)) {
-								left = false;
-								bool v;
-								if (WANT_IDS) {
-									const uint32_t pid = __ldg(I.pos_id + Tp);
-									v = pid != kIdAbsent;
-									s_ids[iw][i] = pid;
-								} else {
-									v = (__ldg(I.valid + (Tp >> 5)) >> (Tp & 31)) & 1u;
-								}
-								if (v) found++; else notfound++;
+						const uint64_t okv = s_okv[wid][run];
+						if (d < 32 && ((okv >> d) & 1)) {
+							bool v;
+							if (WANT_IDS) {
+								const uint64_t Ta = s_T[wid][run];
+								const uint32_t pid = __ldg(I.pos_id + ((s_flag[wid][run] & 2) ? Ta + d : Ta - d));
+								v = pid != kIdAbsent;
+								s_ids[iw][i] = pid;
+							} else {
+								v = (okv >> (32 + d)) & 1;
 							}
+							if (v) found++; else notfound++;
+						} else {
+							left = true;
 						}
 					}
 				}
@@ -398,7 +428,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 		if (WANT_IDS) {
 			// the warp's answers back to the source: one contiguous stream of 32-bit ids over NVLink
 			uint32_t* dst = A.ret[src] + ko0;
-			for (uint32_t t = lane; t < n_ids; t += 32) dst[t] = s_ids[iw][t];
+			if ((uint64_t)ko0 + n_ids <= A.kcap)
+				for (uint32_t t = lane; t < n_ids; t += 32) dst[t] = s_ids[iw][t];
 		}
 	}
 	#pragma unroll
@@ -541,7 +572,8 @@ int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint
 }
 
 int blight_part_lookup(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts, void* const* ret,
-                       uint64_t max_records, uint64_t* d_ctr, void* stream) {
+                       uint64_t cap, uint64_t kcap, uint64_t* d_ctr, void* stream) {
+	const uint64_t max_records = (uint64_t)world * cap;
 	if (!idx || !regions || !d_counts || !d_ctr) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (world == 0 || world > (uint32_t)kMaxRanks) return fail(BL_ERR_INVALID_ARG, "bad world");
 	if (!idx->v.valid) return fail(BL_ERR_INVALID_ARG, "index has no valid-window bitmap");
@@ -550,6 +582,8 @@ int blight_part_lookup(const blight_index* idx, uint32_t world, const void* cons
 	DeviceGuardLite guard(idx->device);
 	OwnerArgs A{};
 	A.world = world;
+	A.cap = cap;
+	A.kcap = kcap;
 	for (uint32_t i = 0; i < world; i++) {
 		A.region[i] = static_cast<const RunRec*>(regions[i]);
 		A.ret[i] = ret ? static_cast<uint32_t*>(ret[i]) : nullptr;
@@ -587,6 +621,8 @@ int blight_peer_alloc(uint64_t bytes, void** d_ptr, unsigned char* handle64) {
 	void* p = nullptr;
 	cudaError_t e = cudaMalloc(&p, bytes);
 	if (e != cudaSuccess) return fail(BL_ERR_NOMEM, std::string("cudaMalloc(peer buffer): ") + cudaGetErrorString(e));
+	e = cudaMemset(p, 0, bytes);  // an inbox slot that was never written must still parse as a (harmless) record
+	if (e != cudaSuccess) { cudaFree(p); return fail(BL_ERR_CUDA, std::string("cudaMemset(peer buffer): ") + cudaGetErrorString(e)); }
 	cudaIpcMemHandle_t h;
 	e = cudaIpcGetMemHandle(&h, p);
 	if (e != cudaSuccess) { cudaFree(p); return fail(BL_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }

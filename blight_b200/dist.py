@@ -346,7 +346,7 @@ class PartitionedSet:
             if want_ids and i > 0:
                 scatter(b ^ 1)
                 pending[b ^ 1] = True
-            api.part_lookup(self.index, self._regions[b], rcv, self._ret_at[b] if want_ids else None, max_rec, ctr)
+            api.part_lookup(self.index, self._regions[b], rcv, self._ret_at[b] if want_ids else None, self._cap, self._kcap, ctr)
         e = self._err.to(torch.int64)
         if world > 1:
             dist.all_reduce(e, op=dist.ReduceOp.MAX, group=self.group)

@@ -195,10 +195,10 @@ int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint
                          uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream);
 /* Owner side: regions[s] = records received from source s (device pointer), d_counts[s] = the packed counter source s
  * accumulated for this owner (DEVICE array: no host round trip), ret[s] = this owner's return region at source s
- * (peer pointer, 32-bit ids, 0xFFFFFFFF = -1; ret == NULL: counting mode). max_records bounds the total for the grid
- * size. d_ctr gets BLIGHT_CTR_FOUND / BLIGHT_CTR_NOT_FOUND (accumulated). */
+ * (peer pointer, 32-bit ids, 0xFFFFFFFF = -1; ret == NULL: counting mode). cap / kcap: records per inbox region and ids
+ * per return region, as in the route (reads and writes never leave them). d_ctr gets BLIGHT_CTR_FOUND / BLIGHT_CTR_NOT_FOUND (accumulated). */
 int blight_part_lookup(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts,
-                       void* const* ret, uint64_t max_records, uint64_t* d_ctr, void* stream);
+                       void* const* ret, uint64_t cap, uint64_t kcap, uint64_t* d_ctr, void* stream);
 /* Back on the source, once every owner has answered: return regions (d_ret: world regions of kcap 32-bit ids, region d
  * written by owner d) -> int64 ids at the slots query_sequence_hash would fill (blight.cpp:575-591), through the side
  * table and the counters the dispatch left. */

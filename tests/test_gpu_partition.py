@@ -131,7 +131,7 @@ def test_three_owners_two_sources_on_one_gpu(tmp_path, torch_cuda):
         cnt_d = counts[:, d].contiguous()
         assert int(cnt_d[2]) == 0 and int(cnt_d[0]) > 0
         ret_ptrs = [ret[s, d].data_ptr() for s in range(2)] + [0]
-        api.part_lookup(owners[d], regions, cnt_d, ret_ptrs, world * cap, ctr)
+        api.part_lookup(owners[d], regions, cnt_d, ret_ptrs, cap, kcap, ctr)
     for s in range(2):
         api.part_scatter(side[s].data_ptr(), cap, counts[s], ret[s].data_ptr(), kcap, world, world * cap, ids_bufs[s])
     torch.cuda.synchronize()
