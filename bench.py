@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ids-only", action="store_true", help="diagnostic: time only the id (hash) mode")
     ap.add_argument("--count-only", action="store_true", help="diagnostic: time only the counting (bool) mode")
+    ap.add_argument("--partition", action="store_true",
+                    help="N > 1: minimizer-bucket partitioned index (BASELINE configs[4]) instead of a replica per GPU; the "
+                         "exchange is fused into the kernels (peer-memory stores over NVLink)")
     return ap.parse_args()
 
 
@@ -191,7 +194,8 @@ def workload_config(args, world):
                     f"{args.reads} simulated {args.read_len} bp reads per GPU per step (1% subst., 50% revcomp), file_query semantics (found / not-found counts; the id mode is reported under ids_mode)",
         "k": args.k, "m": args.m, "n": args.n, "s": args.s, "b": args.b,
         "kmers_per_step_per_gpu": args.reads * (args.read_len - args.k + 1),
-        "parallelism": f"replica x{world}, reads sharded, no data-path collective",
+        "parallelism": (f"partition x{world}: MPHF groups sharded, super-k-mers and ids exchanged as peer-memory stores inside the kernels"
+                        if getattr(args, "partition", False) and world > 1 else f"replica x{world}, reads sharded, no data-path collective"),
         "cache": "inputs (1.5 GB of reads per step) and the index (1.8 GB in HBM) exceed the 126 MB L2; no explicit flush",
     }
 
@@ -219,7 +223,14 @@ def main():
     tmpdir = tempfile.mkdtemp(prefix="blight_bench_")
     g, flat, blob, build_s = build_workload_index(args, rank, world, tmpdir)
     info = flat.info()
-    idx = flat.upload(local)
+    part = None
+    if args.partition and world > 1:
+        from blight_b200 import dist as bdist
+        part = bdist.PartitionedSet.from_full(flat if rank == 0 else None, local, os.path.dirname(blob))
+        part.enable_fused()
+        idx = part.index
+    else:
+        idx = flat.upload(local)
     kpr = args.read_len - args.k + 1
     total_kmers = args.reads * kpr
 
@@ -233,10 +244,18 @@ def main():
     d_ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
 
     def step_count():
-        idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
+        if part is not None:
+            _, c = part.query_reads_fused(d_bases, d_roff, want_ids=False, check_overflow=False)
+            d_ctr.add_(c // world)  # the fused path returns the counters summed over the ranks
+        else:
+            idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
 
     def step_ids():
-        idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
+        if part is not None:
+            _, c = part.query_reads_fused(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, check_overflow=False)
+            d_ctr.add_(c // world)
+        else:
+            idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -283,8 +302,10 @@ def main():
     value = world * total_kmers * args.steps / (ms * 1e-3)
 
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + kernels + D2H inside the timed region ----
+    if part is not None and part.overflowed():
+        raise SystemExit("bench.py --partition: an inbox region overflowed, the timed steps dropped records")
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and part is None:
         h_bases = torch.empty(d_bases.numel(), dtype=torch.uint8, pin_memory=True)
         h_bases.copy_(d_bases)
         h_roff = torch.empty(args.reads + 1, dtype=torch.int64, pin_memory=True)
@@ -345,8 +366,10 @@ def main():
         kernel_ms = ms / args.steps  # the step is exactly one launch of the read kernel per GPU
         achieved = balg * total_kmers / (kernel_ms * 1e-3) / 1e9
         kname = "k_reads_sk<ids>" if headline_ids else "k_reads_sk<count>"
+        if part is not None:
+            kname = "k_dispatch_runs + k_runs_lookup" + (" + k_scatter_runs" if headline_ids else "")
         default_cfg = (args.genome, args.reads, args.read_len, args.k, args.m, args.n, args.b) == (100_000_000, 10_000_000, 150, 31, 7, 5, 6)
-        traffic = ncu_traffic(kname) if default_cfg else None
+        traffic = ncu_traffic(kname) if default_cfg and part is None else None
         line = {
             "metric": "queried k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -358,7 +381,7 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "ids_mode": None if (args.count_only or args.ids_only) else {
                 "value": world * total_kmers * args.steps / (ids_ms * 1e-3), "unit": "k-mers/s", "ms_per_step": ids_ms / args.steps,
-                "kernel": "k_reads_sk<ids>", "note": "query_sequence_hash semantics: one int64 id per k-mer written to HBM (9.6 GB per step)"},
+                "kernel": "k_reads_sk<ids>" if part is None else "k_dispatch_runs + k_runs_lookup + k_scatter_runs", "note": "query_sequence_hash semantics: one int64 id per k-mer written to HBM (9.6 GB per step)"},
             "found_fraction": found_frac, "index": {"number_kmer": info["number_kmer"], "device_bytes": idx.info["device_bytes"],
                                                      "build_seconds": build_s},
         }

@@ -49,6 +49,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    # every rank holds the genome, the whole flat index (replica = ground truth) and its slice on the host for a while:
+    # refuse to start rather than drive the box out of memory
+    need_gb = world * (genome_len * 14e-9 + 2) + genome_len * 10e-9
+    try:
+        import psutil
+        avail_gb = psutil.virtual_memory().available / 1e9
+    except Exception:
+        avail_gb = float("inf")
+    if avail_gb < need_gb:
+        if rank == 0:
+            print(json.dumps({"skipped": f"needs about {need_gb:.0f} GB of host memory, {avail_gb:.0f} GB available"}))
+        dist.destroy_process_group()
+        return
 
     # rank 0 builds the index once and cuts it; everybody loads the whole blob (replica = ground truth) and its slice
     wd = [None]
