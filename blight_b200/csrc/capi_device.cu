@@ -75,6 +75,11 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 	std::vector<DevMphf> mphf(H.n_mphf);
 	uint64_t bits_sectors = 0, pos_sectors = 0;
 	uint32_t small = 1;
+	// exact-position layout (device_index.hpp): fields b bits wider, low bits filled in by the upload pass
+	bool exact = H.b > 0 && H.b <= 8;
+	if (const char* e = getenv("BLIGHT_EXACT_POS")) { if (atoi(e) == 0) exact = false; }
+	for (const MphfRec& r : F.mphf) if (r.present && (r.nbits ? r.nbits : 1) + H.b > 32) exact = false;
+	const uint32_t xb = exact ? H.b : 0;
 	for (uint64_t g = 0; g < H.n_mphf; g++) {
 		const MphfRec& r = F.mphf[g];
 		DevMphf& d = mphf[g];
@@ -84,7 +89,7 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 		d.id_offset = r.id_offset;
 		d.fb_off = r.fb_off;
 		d.fb_count = (uint32_t)r.fb_count;
-		d.nbits = r.nbits ? r.nbits : 1;
+		d.nbits = (r.nbits ? r.nbits : 1) + xb;
 		d.fields_per_sector = 256 / d.nbits;
 		d.fps_magic = (uint32_t)((1ull << 32) / d.fields_per_sector);
 		d.present = r.present;
@@ -119,13 +124,15 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 		// positions: fields_per_sector fields per 32-byte sector, LSB-first inside the sector
 		uint32_t* pd = pos.data() + d.pos_sector_base * 8;
 		const uint32_t nb = d.nbits, fps = d.fields_per_sector;
+		const uint32_t nb_src = r.nbits ? r.nbits : 1;  // width in the flat image
 		for (uint64_t rk = 0; rk < r.nelem; rk++) {
-			const uint64_t bitpos = r.pos_start + rk * nb;
+			const uint64_t bitpos = r.pos_start + rk * nb_src;
 			const uint64_t w0 = F.pos[bitpos >> 6];
 			const uint64_t w1 = ((bitpos >> 6) + 1 < F.pos.size()) ? F.pos[(bitpos >> 6) + 1] : 0;
 			const unsigned sh = unsigned(bitpos & 63);
 			uint64_t v = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
-			v &= (nb >= 64) ? ~0ull : ((1ull << nb) - 1);
+			v &= (nb_src >= 64) ? ~0ull : ((1ull << nb_src) - 1);
+			v <<= xb;  // exact layout: the low b bits start at zero
 			const uint64_t sec = rk / fps;
 			const uint32_t o = uint32_t(rk % fps) * nb;
 			uint32_t* sp = pd + sec * 8;
@@ -181,6 +188,7 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 	v.k = H.k; v.m = H.m; v.b = H.b; v.lb = F.lb();
 	v.kmask = (1ull << (2 * H.k)) - 1;
 	v.small = small;
+	if (exact) v.flags |= kFlagExactPos;
 	{
 		// per-position "answered found" bitmap (+ identifier table, + negative filter): run the lookup core over every
 		// window of every bucket, once. BLIGHT_POS_ID=0 / BLIGHT_FILTER_BITS=0 switch the optional tables off (tuning
@@ -211,7 +219,7 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 			if (ve != cudaSuccess) { blight_index_free(idx); return cuda_fail(ve, "cudaMalloc(filter)"); }
 		}
 		int vrc = launch_window_valid(v, H.n_buckets, H.total_nuc, static_cast<uint32_t*>(idx->d_valid), static_cast<uint32_t*>(idx->d_pos_id),
-		                              static_cast<uint32_t*>(idx->d_filter), fblocks, nullptr);
+		                              static_cast<uint32_t*>(idx->d_filter), fblocks, exact ? static_cast<uint32_t*>(idx->d_pos) : nullptr, nullptr);
 		ve = cudaDeviceSynchronize();
 		if (vrc != BL_OK || ve != cudaSuccess) {
 			blight_index_free(idx);

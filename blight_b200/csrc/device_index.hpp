@@ -12,6 +12,12 @@
 //                  instead of the reference's bit word + rank sample + up to 15 more words.
 //   positions      per group, fields of `nbits` bits packed floor(256/nbits) to a 32-byte sector, never
 //                  straddling a sector (the reference packs them back to back, blight.cpp:464-482).
+//                  With kFlagExactPos (default; BLIGHT_EXACT_POS=0 switches it off) a field is b bits wider and holds the
+//                  position of the k-mer's own window: the high bits are the reference's field (position >> b), the low b
+//                  bits — which the reference gives up and recovers by scanning 2^b windows (blight.cpp:729-740) — are
+//                  OR-ed in at upload by the pass that looks every window up. A lookup then checks that ONE window first
+//                  and only scans the 2^b windows from (field with the low bits cleared) when it does not match, which is
+//                  what the reference does from the start; the answer is the same either way.
 //   sequences      2-bit codes (A0 C1 T2 G3), 16 per u32, FIRST base in the HIGH bits, so a k-mer window is a
 //                  funnel shift of adjacent words (the reference stores one bit per vector<bool> slot,
 //                  blight.cpp:317-318); zero padded past the end for the 2^b-window scan (blight.cpp:732-739).
@@ -41,6 +47,7 @@ namespace blight {
 
 constexpr uint32_t kChunkBits = 224;  // level bits per 32-byte sector
 constexpr uint32_t kFlagFilterAnchors = 1u;  // first k-mers of runs go through the filter too
+constexpr uint32_t kFlagExactPos = 2u;       // position fields hold the exact window (see `positions` above)
 
 struct alignas(64) DevMphf {
 	uint64_t bits_sector_base;  // first sector of this group's level bits (index into DevIndexView::bits, in sectors)

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(kThreads) k_lookup_kmers(DevIndexView I, const
 // The same pass fills pos_id[p] (the identifier itself) and inserts the k-mers of valid windows into the filter.
 template <bool SMALL>
 __global__ void __launch_bounds__(kThreads) k_window_valid(DevIndexView I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* __restrict__ valid,
-                                                           uint32_t* __restrict__ pos_id, uint32_t* __restrict__ filter, uint32_t filter_blocks) {
+                                                           uint32_t* __restrict__ pos_id, uint32_t* __restrict__ filter, uint32_t filter_blocks,
+                                                           uint32_t* pos_rw) {
 	const uint64_t n_round = (total_nuc + 31) & ~31ull;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(kThreads) k_window_valid(DevIndexView I, uint6
 				const uint64_t wv = window_at(I.seq, p, I.k);
 				const uint64_t rc = rc64(wv, I.k);
 				const uint64_t x = wv < rc ? wv : rc;
-				id = lookup_one<SMALL>(I, x, (uint32_t)lo);
+				id = lookup_one<SMALL>(I, x, (uint32_t)lo, nullptr, pos_rw);
 				v = id >= 0;
 				if (v && filter) filter_insert(filter, filter_blocks, x);
 			}
@@ -511,13 +512,13 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
 const char* g_last_cuda_error = "";
 
 int launch_window_valid(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, uint32_t* d_pos_id,
-                        uint32_t* d_filter, uint32_t filter_blocks, cudaStream_t stream) {
+                        uint32_t* d_filter, uint32_t filter_blocks, uint32_t* d_pos_rw, cudaStream_t stream) {
 	if (total_nuc == 0) return 0;
 	const uint64_t want = (total_nuc + kThreads - 1) / kThreads;
 	const uint64_t cap = (uint64_t)sm_count() * 8;
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
-	if (I.small) k_window_valid<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks);
-	else k_window_valid<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks);
+	if (I.small) k_window_valid<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks, d_pos_rw);
+	else k_window_valid<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks, d_pos_rw);
 	g_launches++;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) g_last_cuda_error = cudaGetErrorString(e);

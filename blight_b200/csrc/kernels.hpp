@@ -15,8 +15,10 @@ extern const char* g_last_cuda_error;
 
 // Fills the per-position "window is answered found" bitmap of an uploaded index (see device_index.hpp).
 // d_pos_id / d_filter may be null: the per-position identifier table and the negative filter are filled by the same pass.
+// d_pos_rw: the position sectors, writable, when I.flags has kFlagExactPos (the pass ORs the low b bits of every key's
+// window into its field), else null.
 int launch_window_valid(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, uint32_t* d_pos_id,
-                        uint32_t* d_filter, uint32_t filter_blocks, cudaStream_t stream);
+                        uint32_t* d_filter, uint32_t filter_blocks, uint32_t* d_pos_rw, cudaStream_t stream);
 
 // ids[i] = lookup(canon[i]); d_mini may be null (the minimizer is then computed from the k-mer).
 int launch_lookup_kmers(const DevIndexView& I, const uint64_t* d_canon, const uint32_t* d_mini, uint64_t n, int64_t* d_ids,

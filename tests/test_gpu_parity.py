@@ -134,6 +134,8 @@ print(json.dumps(out))
         {"BLIGHT_READS_KERNEL": "sk", "BLIGHT_POS_ID": "0", "BLIGHT_FILTER_BITS": "0"},  # valid bitmap only
         {"BLIGHT_READS_KERNEL": "sk", "BLIGHT_FILTER_BITS": "3"},                        # many filter false positives
         {"BLIGHT_READS_KERNEL": "sk", "BLIGHT_FILTER_ANCHORS": "0", "BLIGHT_POS_ID": "0"},
+        {"BLIGHT_READS_KERNEL": "plain", "BLIGHT_EXACT_POS": "0"},                       # the reference's truncated positions + 2^b scan only
+        {"BLIGHT_READS_KERNEL": "sk", "BLIGHT_EXACT_POS": "0"},
     ]
     for kern in variants:
         env = dict(os.environ, **kern)
