@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <omp.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -366,10 +367,12 @@ int run_host_reads(const blight_index* idx, const char* text, uint64_t len, cons
 		if ((rc = ws_reserve(idx, 4, (n + 1) * 8, &d_koff)) != BL_OK) return rc;
 		if ((rc = ws_reserve(idx, 5, std::max<uint64_t>(total_kmers, 1) * 8, &d_ids)) != BL_OK) return rc;
 	}
-	CU(cudaMemcpyAsync(d_beg, beg, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-	if (end) CU(cudaMemcpyAsync(d_end, end, n * 8, cudaMemcpyHostToDevice, st));
+	// The read offsets travel with the text, chunk by chunk (80 MB for 10 M reads would otherwise hold the first kernel back
+	// by 1.5 ms). Entries that have not arrived yet read as +infinity, which is what the kernel's search wants them to be:
+	// every read they describe starts past the positions it is looking for.
+	CU(cudaMemsetAsync(d_beg, 0xFF, (n + 1) * 8, st));
 	CU(cudaMemsetAsync(d_ctr, 0, BLIGHT_N_CTR * 8, st));
-	if (ids_out) CU(cudaMemcpyAsync(d_koff, koff, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	uint64_t off_done = 0;  // entries of beg / end / koff already copied
 	// The text goes over in chunks on a second stream; the kernel for chunk c (k-mers starting inside it) waits only
 	// for that chunk (+ a halo), so the copy of chunk c+1 overlaps the lookups of chunk c.
 	cudaStream_t cs = static_cast<cudaStream_t>(idx->copy_stream);
@@ -390,6 +393,17 @@ int run_host_reads(const blight_index* idx, const char* text, uint64_t len, cons
 		if (upto > copied) {
 			CU(cudaMemcpyAsync(static_cast<char*>(d_text) + copied, text + copied, upto - copied, cudaMemcpyHostToDevice, cs));
 			copied = upto;
+		}
+		{
+			// every read that starts before `upto`, and the entry after them
+			const uint64_t need = std::min<uint64_t>(n + 1, uint64_t(std::upper_bound(beg + off_done, beg + n + 1, upto) - beg) + 1);
+			if (need > off_done) {
+				CU(cudaMemcpyAsync(static_cast<uint64_t*>(d_beg) + off_done, beg + off_done, (need - off_done) * 8, cudaMemcpyHostToDevice, cs));
+				if (end && std::min(need, n) > off_done)
+					CU(cudaMemcpyAsync(static_cast<uint64_t*>(d_end) + off_done, end + off_done, (std::min(need, n) - off_done) * 8, cudaMemcpyHostToDevice, cs));
+				if (ids_out) CU(cudaMemcpyAsync(static_cast<uint64_t*>(d_koff) + off_done, koff + off_done, (need - off_done) * 8, cudaMemcpyHostToDevice, cs));
+				off_done = need;
+			}
 		}
 		CU(cudaEventRecord(static_cast<cudaEvent_t>(idx->ev_copy), cs));
 		CU(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(idx->ev_copy), 0));
