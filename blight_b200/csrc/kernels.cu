@@ -2,7 +2,14 @@
 //
 //   k_lookup_kmers   canonical k-mers (+ optional minimizers) -> ids          query_kmer_hash, blight.cpp:545-550
 //   k_reads          ASCII reads -> 2-bit pack -> canonical k-mers + rolling  query_sequence_hash/bool,
-//                    minimizers -> {pairs | ids | counts}                     blight.cpp:554-591; kmer.h:791-810
+//                    minimizers -> {pairs | ids | counts}, one lookup per     blight.cpp:554-591; kmer.h:791-810
+//                    k-mer (the literal formulation)
+//   k_reads_sk       the same path per super-k-mer: first k-mer of a run      + kmer.h:629-693 (super-k-mers)
+//                    through the lookup, the others against one predicted
+//                    window -> {ids | counts | abundance / colour / gather}   + the snippet applications' consumers
+//   k_window_valid   upload-time pass: every window of every bucket through
+//                    the lookup core -> valid / pos_id / filter / exact
+//                    positions (device_index.hpp)
 //
 // k_reads is a persistent kernel of independent warps.  A warp takes strips of kStrip consecutive base positions of
 // the input buffer (strip s -> warp s mod #warps), packs strip+halo bases 2 bits each into its private slice of
