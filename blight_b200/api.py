@@ -27,7 +27,7 @@ SYMBOLS = [
     "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
-    "blight_consume_reads", "blight_gather_reads", "blight_part_dispatch", "blight_part_lookup", "blight_part_scatter", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
+    "blight_consume_reads", "blight_gather_reads", "blight_fasta_cut_stream", "blight_part_dispatch", "blight_part_lookup", "blight_part_scatter", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
 ]
 MAX_RANKS = 16
 RUN_RECORD_BYTES = 32
@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
     L.blight_owner_scatter.argtypes = [vp, vp, u64, vp, u32, u32, vp, vp, vp, vp, vp]
     L.blight_scatter_ids.argtypes = [vp, vp, u64, vp, vp]
     L.blight_launch_count.restype = u64
+    L.blight_fasta_cut_stream.argtypes = [vp, u64, u64, vp, vp, u64, C.POINTER(u64)]
     L.blight_consume_reads.argtypes = [vp, vp, vp, u64, u64, C.c_int, vp, u32, u32, vp, vp]
     L.blight_gather_reads.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp]
     L.blight_part_dispatch.argtypes = [u32, u32, vp, vp, vp, u64, u64, u64, u64, C.POINTER(PartRoute), vp, vp, vp, vp]

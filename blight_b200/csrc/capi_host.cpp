@@ -130,4 +130,29 @@ int blight_flat_slice(const blight_flat* f, uint64_t g_begin, uint64_t g_end, bl
 	return BL_OK;
 }
 
+int blight_fasta_cut_stream(const char* text, uint64_t len, uint64_t chunk_bytes, uint64_t* beg_out, uint64_t* end_out, uint64_t cap,
+                            uint64_t* n_out) {
+	if (!n_out || (len && !text) || chunk_bytes == 0) return fail(BL_ERR_INVALID_ARG, "bad argument");
+	// the loop of stream_file_query (stream_query.cu) on a text in memory: chunks of chunk_bytes, unfinished tail carried
+	std::vector<char> buf;
+	std::vector<uint64_t> nl, beg, end;
+	uint64_t n = 0, file_off = 0, buf_file_off = 0;
+	for (;;) {
+		const uint64_t got = std::min<uint64_t>(chunk_bytes, len - file_off);
+		buf.insert(buf.end(), text + file_off, text + file_off + got);
+		file_off += got;
+		const bool eof = file_off >= len;
+		const size_t n_pairs = fasta_chunk_lines(buf.data(), buf.size(), eof, nl);
+		beg.resize(n_pairs + 1); end.resize(n_pairs + 1);
+		const ChunkCut cut = fasta_chunk_records(buf.size(), eof, nl, beg.data(), end.data());
+		for (size_t i = 0; i < cut.n_rec; i++, n++)
+			if (n < cap && beg_out && end_out) { beg_out[n] = buf_file_off + beg[i]; end_out[n] = buf_file_off + end[i]; }
+		buf.erase(buf.begin(), buf.begin() + cut.consumed);
+		buf_file_off += cut.consumed;
+		if (eof) break;
+	}
+	*n_out = n;
+	return BL_OK;
+}
+
 }  // extern "C"

@@ -3,6 +3,7 @@
 #include "errors.hpp"
 #include "capi_common.hpp"
 
+#include <omp.h>
 #include <zlib.h>
 #include <algorithm>
 #include <cstdio>
@@ -112,6 +113,41 @@ void split_fasta_records(const char* text, uint64_t len, std::vector<SeqView>& s
 		if (n == 0) continue;
 		seqs.push_back(SeqView{s, n});
 	}
+}
+
+size_t fasta_chunk_lines(const char* text, size_t len, bool eof, std::vector<uint64_t>& nl) {
+	// positions of every newline, all host threads
+	const int T = std::max(1, omp_get_max_threads());
+	std::vector<std::vector<uint64_t>> part(T);
+	#pragma omp parallel num_threads(T)
+	{
+		const int t = omp_get_thread_num();
+		const size_t lo = len * t / T, hi = len * (t + 1) / T;
+		std::vector<uint64_t>& v = part[t];
+		v.reserve((hi - lo) / 64 + 16);
+		const char* p = text + lo;
+		const char* e = text + hi;
+		while (p < e) {
+			const char* q = static_cast<const char*>(std::memchr(p, '\n', size_t(e - p)));
+			if (!q) break;
+			v.push_back(uint64_t(q - text));
+			p = q + 1;
+		}
+	}
+	nl.clear();
+	for (auto& v : part) nl.insert(nl.end(), v.begin(), v.end());
+	if (eof && len > 0 && text[len - 1] != '\n') nl.push_back(len);  // the last line needs no terminator
+	return nl.size() / 2;
+}
+
+ChunkCut fasta_chunk_records(size_t len, bool eof, const std::vector<uint64_t>& nl, uint64_t* beg, uint64_t* end) {
+	const size_t n_pairs = nl.size() / 2;
+	ChunkCut c{0, eof ? len : (n_pairs ? size_t(nl[2 * n_pairs - 1]) + 1 : 0)};
+	for (size_t j = 0; j < n_pairs; j++) {
+		const uint64_t hs = j ? nl[2 * j - 1] + 1 : 0, he = nl[2 * j], ss = he + 1, se = nl[2 * j + 1];
+		if (he > hs && se > ss) { beg[c.n_rec] = ss; end[c.n_rec] = se; c.n_rec++; }  // an empty header swallows its line, an empty sequence drops the record
+	}
+	return c;
 }
 
 int read_fasta_records(const std::string& path, std::string& storage, std::vector<SeqView>& seqs, std::string* err) {

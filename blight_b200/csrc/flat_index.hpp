@@ -80,4 +80,15 @@ int read_fasta_records(const std::string& path, std::string& storage, std::vecto
 // Same pairing rule on an in-memory text buffer.
 void split_fasta_records(const char* text, uint64_t len, std::vector<SeqView>& seqs);
 
+// The same pairing on one chunk of a stream (stream_query.cu). Every iteration of the reference's loop consumes exactly
+// two lines, so records are the line pairs (2j, 2j+1) counted from the start of the file: the cut is a parallel newline
+// search plus one pass over the pairs. text[0, len) must start at an even line (the carry of the previous chunk in
+// front); only complete pairs are consumed unless `eof`, where the last line needs no terminator.
+// Two steps so that the caller can size its arrays: fasta_chunk_lines finds the line ends (all host threads) and returns
+// the number of line pairs, an upper bound of the records; fasta_chunk_records fills beg[0..n_rec) / end[0..n_rec) with
+// the sequence lines (offsets into text).
+struct ChunkCut { size_t n_rec, consumed; };
+size_t fasta_chunk_lines(const char* text, size_t len, bool eof, std::vector<uint64_t>& nl);
+ChunkCut fasta_chunk_records(size_t len, bool eof, const std::vector<uint64_t>& nl, uint64_t* beg, uint64_t* end);
+
 }  // namespace blight

@@ -115,32 +115,6 @@ int reserve_offsets(StreamCtx& c, int s, size_t n_rec) {
 	return BL_OK;
 }
 
-// positions of every '\n' of text[0, len), ascending; all host threads
-void find_newlines(const char* text, size_t len, std::vector<uint64_t>& nl) {
-	const int T = std::max(1, omp_get_max_threads());
-	std::vector<std::vector<uint64_t>> part(T);
-	#pragma omp parallel num_threads(T)
-	{
-		const int t = omp_get_thread_num();
-		const size_t lo = len * t / T, hi = len * (t + 1) / T;
-		std::vector<uint64_t>& v = part[t];
-		v.reserve((hi - lo) / 64 + 16);
-		const char* p = text + lo;
-		const char* e = text + hi;
-		while (p < e) {
-			const char* q = static_cast<const char*>(std::memchr(p, '\n', size_t(e - p)));
-			if (!q) break;
-			v.push_back(uint64_t(q - text));
-			p = q + 1;
-		}
-	}
-	size_t total = 0;
-	for (auto& v : part) total += v.size();
-	nl.clear();
-	nl.reserve(total + 1);
-	for (auto& v : part) nl.insert(nl.end(), v.begin(), v.end());
-}
-
 }  // namespace
 
 // file_query(path) without holding the file in memory. ctr[BLIGHT_N_CTR] as blight_query_fasta_host.
@@ -239,24 +213,15 @@ int stream_file_query(const blight_index* idx, const char* path, uint64_t* ctr) 
 		const int s = int(i & 1);
 		// the offsets of chunk i-2 must have left the pinned staging area, its kernel must be done with d_text[s]
 		if ((ce = cudaEventSynchronize(C.done[s])) != cudaSuccess) { rc = cu_fail(ce, "cudaEventSynchronize"); break; }
-		find_newlines(base, len, nl);
-		if (f.eof && len > 0 && base[len - 1] != '\n') nl.push_back(len);  // the last line needs no terminator
-		const size_t n_pairs = nl.size() / 2;
-		const size_t consumed = f.eof ? len : (n_pairs ? size_t(nl[2 * n_pairs - 1]) + 1 : 0);
+		const size_t n_pairs = fasta_chunk_lines(base, len, f.eof, nl);
 		if ((rc = reserve_offsets(C, s, n_pairs)) != BL_OK) break;
+		// beg[0..n_rec], then end[0..n_rec) right behind it: one H2D copy
 		uint64_t* beg = C.h_off[s];
-		size_t n_rec = 0;
-		// first pass: which pairs are records (both lines non-empty), in order
-		{
-			uint64_t* tmp_end = C.h_off[s] + n_pairs + 1;
-			for (size_t j = 0; j < n_pairs; j++) {
-				const uint64_t hs = j ? nl[2 * j - 1] + 1 : 0, he = nl[2 * j], ss = he + 1, se = nl[2 * j + 1];
-				if (he > hs && se > ss) { beg[n_rec] = ss; tmp_end[n_rec] = se; n_rec++; }
-			}
-			beg[n_rec] = len;
-			// end[] goes right behind beg[0..n_rec]
-			if (n_rec != n_pairs) std::memmove(C.h_off[s] + n_rec + 1, tmp_end, n_rec * 8);
-		}
+		uint64_t* end_tmp = C.h_off[s] + n_pairs + 1;
+		const ChunkCut cut = fasta_chunk_records(len, f.eof, nl, beg, end_tmp);
+		const size_t n_rec = cut.n_rec, consumed = cut.consumed;
+		beg[n_rec] = len;
+		std::memmove(C.h_off[s] + n_rec + 1, end_tmp, n_rec * 8);
 		if (!f.eof) carry.assign(base + consumed, base + len); else carry.clear();
 		if (n_rec) {
 			// H2D on the copy stream (after the kernel that last read this device buffer), kernel on the query stream

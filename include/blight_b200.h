@@ -210,6 +210,12 @@ int blight_peer_open(const unsigned char* handle64, void** d_ptr);
 int blight_peer_close(void* d_ptr);
 int blight_peer_free(void* d_ptr);
 
+/* Test hook: the record cut of the streaming file_query (chunks of chunk_bytes, the unfinished tail carried over)
+ * applied to a text in memory; records = sequence lines [beg, end) as file offsets, the reference's pairing rules
+ * (blight.cpp:760-772). *n_out = records found (may exceed cap; only the first cap are stored). */
+int blight_fasta_cut_stream(const char* text, uint64_t len, uint64_t chunk_bytes, uint64_t* beg_out, uint64_t* end_out,
+                            uint64_t cap, uint64_t* n_out);
+
 /* Number of kernel launches issued by this library in the calling process (all threads) since load. */
 uint64_t blight_launch_count(void);
 
