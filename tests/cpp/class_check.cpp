@@ -37,8 +37,9 @@ int main(int argc, char** argv) {
 	std::cout << "number_kmer " << ksl.number_kmer << "\nnumber_super_kmer " << ksl.number_super_kmer << "\n";
 	std::ifstream in(fasta);
 	std::string header, seq;
-	std::getline(in, header);
-	std::getline(in, seq);
+	size_t unitig = 0;
+	while (std::getline(in, header) && std::getline(in, seq) && seq.size() < 250) unitig++;  // first unitig long enough
+	std::cout << "unitig " << unitig << "\n";
 	const std::string read = seq.substr(100, 150);
 	const auto ids = ksl.query_sequence_hash(read);
 	std::cout << "ids_n " << ids.size() << "\nids_first " << ids.front() << "\nids_last " << ids.back() << "\n";

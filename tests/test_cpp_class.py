@@ -60,7 +60,9 @@ def test_class_on_lambda(tmp_path):
     flat = common.build_lambda(7, 5, 3, 6)
     port = common.cport_of(flat, tmp_path)
     bases, offs = fixtures.lambda_unitigs()
-    want = port.query_sequence(bases[100:250])
+    u = int(f["unitig"])
+    assert int(offs[u + 1] - offs[u]) >= 250 and all(int(offs[i + 1] - offs[i]) < 250 for i in range(u))
+    want = port.query_sequence(bases[int(offs[u]) + 100:int(offs[u]) + 250])
     assert f["ids_n"] == "120" and int(f["ids_first"]) == int(want[0]) and int(f["ids_last"]) == int(want[-1])
     assert f["bool"] == "120 0" and f["absent_kmer"] == "-1"
     assert f["file_query"] == "48462 0"
