@@ -389,6 +389,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    import shutil
+    shutil.rmtree(tmpdir, ignore_errors=True)  # rank 0's holds the index blob (and the slices of --partition)
 
 
 if __name__ == "__main__":

@@ -156,6 +156,9 @@ def main():
         assert ok, out
     dist.barrier()
     dist.destroy_process_group()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(wd[0], ignore_errors=True)
 
 
 if __name__ == "__main__":
