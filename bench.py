@@ -159,7 +159,7 @@ def run_reference(args, rank):
     import oracle
     from blight_b200 import api, synth
     if not oracle.reference_available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libblight_ref.so was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libblight_ref.so was not built (needs /root/reference at build time)"})
         return
     with tempfile.TemporaryDirectory() as td:
         g, flat, blob, _ = build_workload_index(args, 0, 1, td)
@@ -185,7 +185,7 @@ def run_reference(args, rank):
         "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "found": f, "not_found": nf,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
@@ -200,7 +200,25 @@ def workload_config(args, world):
     }
 
 
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its version banner there)
+    is sent to stderr, and the line goes to the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+OUT = None
+
+
+def emit(line: dict):
+    print(json.dumps(line), file=OUT or sys.stdout, flush=True)
+
+
 def main():
+    global OUT
+    OUT = claim_stdout()
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -385,7 +403,7 @@ def main():
             "found_fraction": found_frac, "index": {"number_kmer": info["number_kmer"], "device_bytes": idx.info["device_bytes"],
                                                      "build_seconds": build_s},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
