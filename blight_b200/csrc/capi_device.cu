@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "capi_common.hpp"
@@ -102,7 +103,9 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 		}
 	}
 	std::vector<uint32_t> bits((bits_sectors + 1) * 8, 0), pos((pos_sectors + 1) * 8, 0);
-	#pragma omp parallel for schedule(dynamic, 1)
+	// launchers such as torchrun export OMP_NUM_THREADS=1; the re-layout of a large index should not crawl because of it
+	const int relayout_threads = std::max(omp_get_max_threads(), std::min(8, (int)std::thread::hardware_concurrency()));
+	#pragma omp parallel for schedule(dynamic, 1) num_threads(relayout_threads)
 	for (uint64_t g = 0; g < H.n_mphf; g++) {
 		const MphfRec& r = F.mphf[g];
 		if (!r.present) continue;
@@ -148,7 +151,7 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 	{
 		const uint32_t* src = reinterpret_cast<const uint32_t*>(F.seq.data());
 		const int64_t n32 = (int64_t)H.seq_words * 2;
-		#pragma omp parallel for schedule(static)
+		#pragma omp parallel for schedule(static) num_threads(relayout_threads)
 		for (int64_t i = 0; i < n32; i++) seq[i] = bitrev32(src[i]);
 	}
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <thread>
 
 namespace blight {
 
@@ -117,7 +118,7 @@ void split_fasta_records(const char* text, uint64_t len, std::vector<SeqView>& s
 
 size_t fasta_chunk_lines(const char* text, size_t len, bool eof, std::vector<uint64_t>& nl) {
 	// positions of every newline, all host threads
-	const int T = std::max(1, omp_get_max_threads());
+	const int T = std::max(omp_get_max_threads(), std::min(8, (int)std::thread::hardware_concurrency()));  // OMP_NUM_THREADS=1 launchers
 	std::vector<std::vector<uint64_t>> part(T);
 	#pragma omp parallel num_threads(T)
 	{
