@@ -37,7 +37,6 @@ namespace {
 constexpr int kMaxRanks = BLIGHT_MAX_RANKS;
 constexpr int kRecWords = 5;                  // 4 words of bases + one zero word for the funnel
 constexpr uint32_t kMaxRecKmers = 25;         // k-mers per record (k - m + 1 of the usual shapes): bounds a warp's staging
-constexpr int kMaxPairs = 32 * (kMaxRecKmers - 1);
 constexpr int kMaxIds = 32 * kMaxRecKmers;
 constexpr int kResCap = 128;                  // entries of a warp's work list (drained whenever fewer than 32 slots are left)
 constexpr unsigned long long kKmerBits = 40;  // packed pair counter: slots << 40 | k-mers
