@@ -329,24 +329,52 @@ class PartitionedSet:
             self._ev_scat[b].record(side)
 
         pending = [False, False]
-        for i in range(n_sub):
+
+        def dispatch(i):
             b = i & 1
-            cnt, rcv = self._counts[b], self._recv_counts[b]
             if pending[b]:
                 main.wait_event(self._ev_scat[b])  # the scatter of sub-batch i-2 still reads this buffer's counters and side table
                 pending[b] = False
-            cnt.zero_()
+            self._counts[b].zero_()
             if i * self._sub < total:
-                api.part_dispatch(self.k, self.m, bases, read_off, koff, self._routes[b], cnt, ctr, self._err,
+                api.part_dispatch(self.k, self.m, bases, read_off, koff, self._routes[b], self._counts[b], ctr, self._err,
                                   i * self._sub, min(total, (i + 1) * self._sub))
+
+        def exchange(i):
+            b = i & 1
             if world > 1:
-                dist.all_to_all_single(rcv, cnt, group=self.group)
-            else:
-                rcv = cnt
-            if want_ids and i > 0:
-                scatter(b ^ 1)
-                pending[b ^ 1] = True
+                dist.all_to_all_single(self._recv_counts[b], self._counts[b], group=self.group)
+                return self._recv_counts[b]
+            return self._counts[b]
+
+        def lookup(i, rcv):
+            b = i & 1
             api.part_lookup(self.index, self._regions[b], rcv, self._ret_at[b] if want_ids else None, self._cap, self._kcap, ctr)
+
+        if os.environ.get("BLIGHT_PART_ORDER") == "ahead":
+            # experimental order (not measured at N = 8 yet): dispatch(i+1) is issued before lookup(i), so by the time the
+            # counter exchange of i+1 is entered every rank's dispatch is long done and the barrier only sees lookup skew
+            rcv = None
+            if n_sub > 0:
+                dispatch(0)
+                rcv = exchange(0)
+            for i in range(n_sub):
+                if want_ids and i > 0:
+                    scatter((i - 1) & 1)
+                    pending[(i - 1) & 1] = True
+                if i + 1 < n_sub:
+                    dispatch(i + 1)
+                lookup(i, rcv)
+                if i + 1 < n_sub:
+                    rcv = exchange(i + 1)
+        else:
+            for i in range(n_sub):
+                dispatch(i)
+                rcv = exchange(i)
+                if want_ids and i > 0:
+                    scatter((i - 1) & 1)
+                    pending[(i - 1) & 1] = True
+                lookup(i, rcv)
         e = self._err.to(torch.int64)
         if world > 1:
             dist.all_reduce(e, op=dist.ReduceOp.MAX, group=self.group)

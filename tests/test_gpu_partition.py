@@ -27,7 +27,7 @@ def _dev_batch(torch, rb, ro, k=31):
 
 
 @pytest.mark.parametrize("shape", [(9, 6, 6), (7, 5, 0), (11, 8, 8)])
-def test_loopback_partition_matches_oracle(shape, tmp_path, torch_cuda):
+def test_loopback_partition_matches_oracle(shape, tmp_path, torch_cuda, monkeypatch):
     torch = torch_cuda
     m, n, b = shape
     g, ub, uo, rb, ro = common.synthetic(600_000, 6000, seed=11 + m, sub_rate=0.03)
@@ -48,6 +48,11 @@ def test_loopback_partition_matches_oracle(shape, tmp_path, torch_cuda):
     _, ctr2 = ps.query_reads_fused(d_b, d_o, want_ids=False)
     torch.cuda.synchronize()
     assert torch.equal(ctr2.cpu(), ctr.cpu())
+    # the experimental kernel order (dispatch of the next sub-batch ahead of the lookup of this one): same answers
+    monkeypatch.setenv("BLIGHT_PART_ORDER", "ahead")
+    ids3, ctr3 = ps.query_reads_fused(d_b, d_o, d_k, total)
+    torch.cuda.synchronize()
+    assert np.array_equal(ids3.cpu().numpy(), want) and torch.equal(ctr3.cpu(), ctr.cpu())
 
 
 def test_loopback_ragged_and_tiny_reads(tmp_path, torch_cuda):
