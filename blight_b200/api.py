@@ -23,7 +23,7 @@ CTR_FOUND, CTR_NOT_FOUND, CTR_QUERIES, CTR_INVALID, N_CTR = 0, 1, 2, 3, 4
 SYMBOLS = [
     "blight_version", "blight_last_error", "blight_check_params", "blight_flat_build_file", "blight_flat_build_seqs", "blight_flat_build_spans",
     "blight_flat_save", "blight_flat_load", "blight_flat_free", "blight_flat_info", "blight_flat_compare",
-    "blight_flat_slice", "blight_flat_group_sizes", "blight_index_upload", "blight_index_free", "blight_index_info",
+    "blight_flat_slice", "blight_flat_group_sizes", "blight_index_upload", "blight_index_upload_opts", "blight_index_free", "blight_index_info",
     "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
@@ -51,12 +51,29 @@ class InvalidBase(BlightError, ValueError):
 
 
 class Info(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("k", "m", "n_log2", "s_log2", "b", "reserved")] + [
+    _fields_ = [(n, C.c_uint32) for n in ("k", "m", "n_log2", "s_log2", "b", "layout")] + [
         (n, C.c_uint64) for n in ("n_buckets", "n_mphf", "number_kmer", "number_super_kmer", "total_nuc", "positions_bits",
-                                  "mphf_bits", "fallback_keys", "largest_mphf", "largest_bucket", "device_bytes")]
+                                  "mphf_bits", "fallback_keys", "largest_mphf", "largest_bucket", "device_bytes", "id_base")]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+LAYOUT_POS_ID, LAYOUT_FILTER, LAYOUT_EXACT_POS = 1, 2, 4
+
+
+class UploadOptions(C.Structure):
+    """blight_upload_options (include/blight_b200.h): 1 = on, 0 = off, -1 = library default."""
+    _fields_ = [("struct_size", C.c_uint32), ("pos_id", C.c_int32), ("filter_bits", C.c_int32), ("exact_pos", C.c_int32),
+                ("filter_anchors", C.c_int32)]
+
+    def __init__(self, pos_id=-1, filter_bits=-1, exact_pos=-1, filter_anchors=-1):
+        super().__init__(C.sizeof(UploadOptions), pos_id, filter_bits, exact_pos, filter_anchors)
+
+    @classmethod
+    def compact(cls) -> "UploadOptions":
+        """Only the reference's own arrays re-laid out (+ 1 bit per base): ~30 bits per k-mer instead of ~160."""
+        return cls(0, 0, 0, 0)
 
 
 _lib = None
@@ -87,6 +104,7 @@ def lib() -> C.CDLL:
     L.blight_flat_slice.argtypes = [vp, u64, u64, C.POINTER(vp)]
     L.blight_flat_group_sizes.argtypes = [vp, vp]
     L.blight_index_upload.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.blight_index_upload_opts.argtypes = [vp, C.c_int, vp, C.POINTER(vp)]
     L.blight_index_free.argtypes = [vp]
     L.blight_index_free.restype = None
     L.blight_index_info.argtypes = [vp, C.POINTER(Info)]
@@ -108,7 +126,7 @@ def lib() -> C.CDLL:
     L.blight_gather_reads.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp]
     L.blight_part_dispatch.argtypes = [u32, u32, vp, vp, vp, u64, u64, u64, u64, C.POINTER(PartRoute), vp, vp, vp, vp]
     L.blight_part_lookup.argtypes = [vp, u32, C.POINTER(vp), vp, C.POINTER(vp), u64, u64, vp, vp]
-    L.blight_part_scatter.argtypes = [vp, u64, vp, vp, u64, u32, u64, vp, vp]
+    L.blight_part_scatter.argtypes = [vp, u64, vp, vp, u64, u32, u64, vp, vp, vp]
     L.blight_peer_alloc.argtypes = [u64, C.POINTER(vp), C.c_char_p]
     L.blight_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.blight_peer_close.argtypes = [vp]
@@ -196,9 +214,12 @@ class FlatIndex:
         _check(lib().blight_flat_slice(self._h, g_begin, g_end, C.byref(h)))
         return FlatIndex(h.value)
 
-    def upload(self, device: int = 0) -> "DeviceIndex":
+    def upload(self, device: int = 0, options: Optional["UploadOptions"] = None) -> "DeviceIndex":
         h = C.c_void_p()
-        _check(lib().blight_index_upload(self._h, device, C.byref(h)))
+        if options is None:
+            _check(lib().blight_index_upload(self._h, device, C.byref(h)))
+        else:
+            _check(lib().blight_index_upload_opts(self._h, device, C.addressof(options), C.byref(h)))
         return DeviceIndex(h.value, device)
 
     def __del__(self):
@@ -402,9 +423,10 @@ def part_lookup(index: "DeviceIndex", regions: Sequence[int], counts, ret_ptrs: 
     _check(lib().blight_part_lookup(index._h, world, reg, _ptr(counts), retp, cap, kcap, _ptr(ctr), _stream_handle(stream)))
 
 
-def part_scatter(side_ptr: int, cap: int, counts, ret_ptr: int, kcap: int, world: int, max_records: int, ids, stream=None):
-    """Source side, after the owners answered: return regions -> int64 ids in read order."""
-    _check(lib().blight_part_scatter(side_ptr, cap, _ptr(counts), ret_ptr, kcap, world, max_records, _ptr(ids), _stream_handle(stream)))
+def part_scatter(side_ptr: int, cap: int, counts, ret_ptr: int, kcap: int, world: int, max_records: int, ids, id_bases=None, stream=None):
+    """Source side, after the owners answered: return regions -> int64 ids in read order. id_bases: first identifier of
+    every owner's slice (numpy uint64, world entries); owners return slice-local 32-bit ids."""
+    _check(lib().blight_part_scatter(side_ptr, cap, _ptr(counts), ret_ptr, kcap, world, max_records, _ptr(id_bases), _ptr(ids), _stream_handle(stream)))
 
 
 def reads_to_kmers(k: int, m: int, bases, read_off, kmer_off, total_kmers: int, stream=None):

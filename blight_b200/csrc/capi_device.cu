@@ -58,7 +58,22 @@ int ensure_device(int device) {
 extern "C" {
 
 int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
+	return blight_index_upload_opts(ff, device, nullptr, out);
+}
+
+int blight_index_upload_opts(const blight_flat* ff, int device, const blight_upload_options* opts, blight_index** out) {
 	if (!ff || !out) return fail(BL_ERR_INVALID_ARG, "null argument");
+	if (opts && opts->struct_size != sizeof(blight_upload_options)) return fail(BL_ERR_INVALID_ARG, "blight_upload_options.struct_size");
+	// -1 = library default; the environment knobs of DESIGN.md (tests, experiments) only replace defaults
+	auto knob = [](int32_t asked, const char* env, int32_t dflt) {
+		if (asked >= 0) return asked;
+		const char* e = getenv(env);
+		return e ? (int32_t)atoi(e) : dflt;
+	};
+	const int32_t o_pos_id = knob(opts ? opts->pos_id : -1, "BLIGHT_POS_ID", 1);
+	const int32_t o_filter_bits = knob(opts ? opts->filter_bits : -1, "BLIGHT_FILTER_BITS", 20);
+	const int32_t o_exact = knob(opts ? opts->exact_pos : -1, "BLIGHT_EXACT_POS", 1);
+	const int32_t o_anchors = knob(opts ? opts->filter_anchors : -1, "BLIGHT_FILTER_ANCHORS", 1);
 	int rc = ensure_device(device);
 	if (rc != BL_OK) return rc;
 	const FlatIndex& F = ff->f;
@@ -78,8 +93,13 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 	uint64_t bits_sectors = 0, pos_sectors = 0;
 	uint32_t small = 1;
 	// exact-position layout (device_index.hpp): fields b bits wider, low bits filled in by the upload pass
-	bool exact = H.b > 0 && H.b <= 8;
-	if (const char* e = getenv("BLIGHT_EXACT_POS")) { if (atoi(e) == 0) exact = false; }
+	uint64_t n_keys = 0, max_id = 0, min_id = ~0ull;
+	for (const MphfRec& r : F.mphf)
+		if (r.present) { n_keys += r.nelem; max_id = std::max<uint64_t>(max_id, r.id_offset + r.nelem); min_id = std::min<uint64_t>(min_id, r.id_offset); }
+	if (n_keys == 0) min_id = max_id = 0;
+	const uint64_t n_local = max_id - min_id;  // identifiers of this index (or slice) span [min_id, max_id)
+	const bool lid_fits = n_local < 0xFFFFFFFFull && H.total_nuc > 0;
+	bool exact = o_exact != 0 && H.b > 0 && H.b <= 8 && lid_fits;
 	for (const MphfRec& r : F.mphf) if (r.present && (r.nbits ? r.nbits : 1) + H.b > 32) exact = false;
 	const uint32_t xb = exact ? H.b : 0;
 	for (uint64_t g = 0; g < H.n_mphf; g++) {
@@ -194,57 +214,77 @@ int blight_index_upload(const blight_flat* ff, int device, blight_index** out) {
 	v.small = small;
 	if (exact) v.flags |= kFlagExactPos;
 	{
-		// per-position "answered found" bitmap (+ identifier table, + negative filter): run the lookup core over every
-		// window of every bucket, once. BLIGHT_POS_ID=0 / BLIGHT_FILTER_BITS=0 switch the optional tables off (tuning
-		// and tests); BLIGHT_FILTER_BITS=n sizes the filter at n bits per k-mer (default 20: a false
-		// positive is a whole lookup of an absent key, whose BBHash level walk holds its warp back; measured 38.2 / 35.4 /
-		// 34.6 / 34.3 / 34.2 ms per 1.2 G k-mers at 8 / 12 / 16 / 20 / 32 bits).
+		// Derived tables (device_index.hpp): per-position "answered found" bitmap, per-position identifier table, negative filter,
+		// exact positions — the lookup core run once over every window of the index text. Only the bitmap is required: when
+		// HBM is short the optional tables are left out (blight_info.layout says what is there) and the kernels take the
+		// paths that do without them.
 		const size_t vbytes = ((size_t)(H.total_nuc + 31) / 32 + 1) * 4;
 		cudaError_t ve = cudaMalloc(&idx->d_valid, vbytes);
 		if (ve == cudaSuccess) ve = cudaMemset(idx->d_valid, 0, vbytes);
 		if (ve != cudaSuccess) { blight_index_free(idx); return cuda_fail(ve, "cudaMalloc(valid bitmap)"); }
-		uint64_t n_keys = 0, max_id = 0;
-		for (const MphfRec& r : F.mphf) if (r.present) { n_keys += r.nelem; max_id = std::max<uint64_t>(max_id, r.id_offset + r.nelem); }
-		const char* e_pid = getenv("BLIGHT_POS_ID");
-		const char* e_fb = getenv("BLIGHT_FILTER_BITS");
-		const bool want_pid = !(e_pid && atoi(e_pid) == 0) && max_id < 0xFFFFFFFFull && H.total_nuc > 0;
-		const uint64_t fbits = e_fb ? strtoull(e_fb, nullptr, 10) : 20;
+		v.id_base = min_id;  // the per-position table holds id - id_base (32 bits)
+		const bool want_pid = o_pos_id != 0 && lid_fits;
 		size_t pbytes = 0, fbytes = 0;
 		uint32_t fblocks = 0;
+		auto soft_fail = [](cudaError_t e) { if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return true; } return false; };
 		if (want_pid) {
 			pbytes = ((size_t)H.total_nuc + 32) * 4;
 			ve = cudaMalloc(&idx->d_pos_id, pbytes);
-			if (ve != cudaSuccess) { blight_index_free(idx); return cuda_fail(ve, "cudaMalloc(position -> id table)"); }
+			if (ve != cudaSuccess) {
+				if (!soft_fail(ve)) { blight_index_free(idx); return cuda_fail(ve, "cudaMalloc(position -> id table)"); }
+				idx->d_pos_id = nullptr; pbytes = 0;
+			}
 		}
-		if (fbits && n_keys) {
-			const uint64_t nb = std::min<uint64_t>((n_keys * fbits + 255) / 256 + 1, 0xFFFFFFFFull);
+		if (o_filter_bits > 0 && n_keys) {
+			const uint64_t nb = std::min<uint64_t>((n_keys * (uint64_t)o_filter_bits + 255) / 256 + 1, 0xFFFFFFFFull);
 			fblocks = (uint32_t)nb;
 			fbytes = (size_t)nb * 32;
 			ve = cudaMalloc(&idx->d_filter, fbytes);
 			if (ve == cudaSuccess) ve = cudaMemset(idx->d_filter, 0, fbytes);
-			if (ve != cudaSuccess) { blight_index_free(idx); return cuda_fail(ve, "cudaMalloc(filter)"); }
+			if (ve != cudaSuccess) {
+				if (!soft_fail(ve)) { blight_index_free(idx); return cuda_fail(ve, "cudaMalloc(filter)"); }
+				cudaFree(idx->d_filter); idx->d_filter = nullptr; fbytes = 0; fblocks = 0;
+			}
 		}
-		int vrc = launch_window_valid(v, H.n_buckets, H.total_nuc, static_cast<uint32_t*>(idx->d_valid), static_cast<uint32_t*>(idx->d_pos_id),
-		                              static_cast<uint32_t*>(idx->d_filter), fblocks, exact ? static_cast<uint32_t*>(idx->d_pos) : nullptr, nullptr);
+		// scratch of the exact-position passes: candidate bitmap, one claim word per key, and (without the identifier table)
+		// a per-position identifier array that lives only during the upload
+		void *d_cand = nullptr, *d_claim = nullptr, *d_lid_tmp = nullptr;
+		if (exact) {
+			bool ok = cudaMalloc(&d_cand, vbytes) == cudaSuccess && cudaMalloc(&d_claim, (size_t)(n_local + 1) * 4) == cudaSuccess;
+			if (ok && !idx->d_pos_id) ok = cudaMalloc(&d_lid_tmp, ((size_t)H.total_nuc + 32) * 4) == cudaSuccess;
+			if (ok) ok = cudaMemset(d_cand, 0, vbytes) == cudaSuccess && cudaMemset(d_claim, 0xFF, (size_t)(n_local + 1) * 4) == cudaSuccess;
+			if (!ok) {
+				// no room for the scratch: keep the (already widened) fields with zero low bits — every lookup then starts its scan at
+				// the reference's own truncated position, which is exact as well
+				cudaGetLastError();
+				cudaFree(d_cand); cudaFree(d_claim); cudaFree(d_lid_tmp);
+				d_cand = d_claim = d_lid_tmp = nullptr;
+			}
+		}
+		uint32_t* d_lid = idx->d_pos_id ? static_cast<uint32_t*>(idx->d_pos_id) : static_cast<uint32_t*>(d_lid_tmp);
+		int vrc = launch_window_answers(v, H.n_buckets, H.total_nuc, static_cast<uint32_t*>(idx->d_valid), d_lid, static_cast<uint32_t*>(d_cand),
+		                                static_cast<uint32_t*>(idx->d_filter), fblocks, nullptr);
+		if (vrc == BL_OK && exact && d_cand)
+			vrc = launch_exact_positions(v, H.n_buckets, H.n_mphf, H.total_nuc, static_cast<const uint32_t*>(d_cand), d_lid,
+			                             static_cast<uint32_t*>(d_claim), static_cast<uint32_t*>(idx->d_pos), nullptr);
 		ve = cudaDeviceSynchronize();
+		cudaFree(d_cand); cudaFree(d_claim); cudaFree(d_lid_tmp);
 		if (vrc != BL_OK || ve != cudaSuccess) {
 			blight_index_free(idx);
-			return fail(BL_ERR_CUDA, std::string("valid-window kernel failed: ") + (ve != cudaSuccess ? cudaGetErrorString(ve) : g_last_cuda_error));
+			return fail(BL_ERR_CUDA, std::string("upload passes failed: ") + (ve != cudaSuccess ? cudaGetErrorString(ve) : g_last_cuda_error));
 		}
 		v.pos_id = static_cast<const uint32_t*>(idx->d_pos_id);
 		v.filter = static_cast<const uint32_t*>(idx->d_filter);
 		v.filter_blocks = fblocks;
-		{
-			// anchors through the filter too: measured 51.1 vs 52.0 ms (counting) and 56.8 vs 57.9 ms (ids) per 1.2 G k-mers
-			const char* e = getenv("BLIGHT_FILTER_ANCHORS");
-			if (!e || atoi(e)) v.flags |= kFlagFilterAnchors;
-		}
+		if (o_anchors) v.flags |= kFlagFilterAnchors;  // anchors through the filter too: measured 51.1 vs 52.0 ms (counting), 56.8 vs 57.9 ms (ids)
 		bytes += pbytes + fbytes;
 		v.valid = static_cast<const uint32_t*>(idx->d_valid);
 		bytes += vbytes;
 	}
 	fill_info(F, &idx->info);
 	idx->info.device_bytes = bytes;
+	idx->info.layout = (idx->v.pos_id ? BLIGHT_LAYOUT_POS_ID : 0u) | (idx->v.filter ? BLIGHT_LAYOUT_FILTER : 0u) |
+	                   ((idx->v.flags & kFlagExactPos) ? BLIGHT_LAYOUT_EXACT_POS : 0u);
 	*out = idx;
 	return BL_OK;
 }

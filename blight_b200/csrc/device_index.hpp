@@ -15,7 +15,8 @@
 //                  With kFlagExactPos (default; BLIGHT_EXACT_POS=0 switches it off) a field is b bits wider and holds the
 //                  position of the k-mer's own window: the high bits are the reference's field (position >> b), the low b
 //                  bits — which the reference gives up and recovers by scanning 2^b windows (blight.cpp:729-740) — are
-//                  OR-ed in at upload by the pass that looks every window up. A lookup then checks that ONE window first
+//                  filled in at upload from the pass that looks every window up (one owner per field, kernels.cu:
+//                  k_claim_low). A lookup then checks that ONE window first
 //                  and only scans the 2^b windows from (field with the low bits cleared) when it does not match, which is
 //                  what the reference does from the start; the answer is the same either way.
 //   sequences      2-bit codes (A0 C1 T2 G3), 16 per u32, FIRST base in the HIGH bits, so a k-mer window is a
@@ -27,14 +28,18 @@
 //                  the lookup core itself on every window. It lets a query whose neighbour in the read was found at
 //                  position T check the window at T+-1 and, on a match, skip the position read and the 2^b scan while
 //                  still answering exactly as the reference would (including its junction-window false positives).
-//   pos_id         (optional, N < 2^32-1) 1 x u32 per base position p: the identifier the reference returns for the k-mer
-//                  spelled by the window at p (0xFFFFFFFF when it answers -1), computed by the same pass as `valid`. The
+//   pos_id         (optional, fewer than 2^32-1 k-mers in this index or slice) 1 x u32 per base position p: the identifier the
+//                  reference returns for the k-mer spelled by the window at p, minus id_base (the first identifier of the
+//                  slice); 0xFFFFFFFF when it answers -1. Computed by the same pass as `valid`. The
 //                  k-mers of a super-k-mer sit at consecutive positions, so the ids of a run are ONE or two sectors
 //                  instead of (levels + rank) sectors per k-mer.
-//   filter         register-blocked Bloom filter over V = {canonical k-mers spelled by the valid windows} (every k-mer the
-//                  reference answers "found" is in V: it matched a window, and that window's valid bit is its own
-//                  answer). One 32-byte sector per key, one probe bit in each of its 8 words. No false negatives, so a
-//                  miss proves "-1" with a single sector read; a hit (true or false positive) takes the whole lookup.
+//   filter         register-blocked Bloom filter over V = {canonical k-mers x spelled by ANY window of the text (the 2^b windows
+//                  past its end included) for which the reference answers "found" when x is routed to ITS OWN minimizer's
+//                  bucket}. Every k-mer the reference answers "found" equals some window of the text — also one that starts
+//                  past the end of the bucket it was routed to, because the 2^b scan never re-checks the bucket length
+//                  (blight.cpp:732-739) — so it is in V. One 32-byte sector per key, one probe bit in each of its 8 words. No
+//                  false negatives, so a miss proves "-1" with a single sector read; a hit (true or false positive) takes
+//                  the whole lookup.
 #pragma once
 #include <cstdint>
 
@@ -79,6 +84,7 @@ struct DevIndexView {
 	uint32_t filter_blocks;
 	uint32_t flags;         // kFlagFilterAnchors
 	uint64_t kmask;
+	uint64_t id_base;       // pos_id holds id - id_base: the identifiers of a slice (partition mode) start here
 	uint32_t k, m, b, lb;
 	uint32_t small;  // every MPHF group has fewer than 2^32 level bits: 32-bit bit arithmetic in the probe
 };

@@ -183,6 +183,9 @@ void fill_info(const FlatIndex& f, blight_info* out) {
 	out->fallback_keys = h.fallback_total;
 	for (const MphfRec& r : f.mphf) out->largest_mphf = r.nelem > out->largest_mphf ? r.nelem : out->largest_mphf;
 	for (uint32_t n : f.bucket_nuc) out->largest_bucket = n > out->largest_bucket ? n : out->largest_bucket;
+	uint64_t base = ~0ull;
+	for (const MphfRec& r : f.mphf) if (r.present && r.id_offset < base) base = r.id_offset;
+	out->id_base = base == ~0ull ? 0 : base;
 }
 
 namespace {

@@ -46,40 +46,122 @@ __global__ void __launch_bounds__(kThreads) k_lookup_kmers(DevIndexView I, const
 	}
 }
 
-// valid[p] = the reference answers "found" for the k-mer spelled by the window at base position p when the query is
-// routed to p's own bucket (device_index.hpp). One thread per position, one ballot word per warp.
-// The same pass fills pos_id[p] (the identifier itself) and inserts the k-mers of valid windows into the filter.
+// ---- the upload-time passes over every window of the index text (device_index.hpp: valid / pos_id / filter / exact positions) ----
+//
+// k_window_answers   one thread per base position p (every window start the reference's scan can reach: the text plus the
+//                    2^b windows past its end, which read as zero padding):
+//                      x  = canonical k-mer spelled by the window at p
+//                      own answer   lookup(x routed to p's OWN bucket)     -> valid[p], pos_id[p]   (what a query predicted
+//                                   to sit at p receives: it has the bucket's minimizer, k_reads_sk C3)
+//                      true answer  lookup(x routed to minimizer(x))       -> filter insert when found
+//                    The two differ for windows that span two super-k-mers of a bucket ("junction" windows) and whose k-mer
+//                    has another minimizer: the reference's 2^b scan (blight.cpp:732-739) never re-checks the bucket length,
+//                    so a query routed to bucket B can match a window that starts in a FOLLOWING bucket. Every k-mer the
+//                    reference answers "found" matched some window of the text, hence is inserted here: the filter has no
+//                    false negatives with respect to the reference's answers.
+//                    cand[p]: the own answer matched at p itself and x has the bucket's minimizer: p may own the low bits of
+//                    its position field.
+// k_claim_low        exact-position layout: among the candidate windows that hit the same position field (the key the MPHF
+//                    was built on, plus alien junction k-mers that collide on its rank) ONE gets the field's low b bits:
+//                    windows with a candidate neighbour first (keys inside a super-k-mer; aliens sit among windows that are
+//                    mostly not found), then the smallest offset. Deterministic: atomicMin over (priority, offset).
+// k_write_low        the winner ORs its offset into the (zero) low bits. Nothing reads `pos` in this kernel.
 template <bool SMALL>
-__global__ void __launch_bounds__(kThreads) k_window_valid(DevIndexView I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* __restrict__ valid,
-                                                           uint32_t* __restrict__ pos_id, uint32_t* __restrict__ filter, uint32_t filter_blocks,
-                                                           uint32_t* pos_rw) {
-	const uint64_t n_round = (total_nuc + 31) & ~31ull;
+__global__ void __launch_bounds__(kThreads) k_window_answers(DevIndexView I, uint64_t n_buckets, uint64_t total_nuc, uint64_t n_scan,
+                                                             uint32_t* __restrict__ valid, uint32_t* __restrict__ pos_id, uint32_t* __restrict__ cand,
+                                                             uint32_t* __restrict__ filter, uint32_t filter_blocks) {
+	const uint64_t n_round = (n_scan + 31) & ~31ull;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
-		bool v = false;
-		int64_t id = -1;
-		if (p < total_nuc) {
-			// last bucket whose start is <= p: the non-empty bucket holding p (empty ones share their successor's start)
-			uint64_t lo = 0, hi = n_buckets - 1;
-			while (lo < hi) {
-				const uint64_t mid = (lo + hi + 1) >> 1;
-				const uint4 bd = __ldg(I.bucket + mid);
-				if ((((uint64_t)bd.y << 32) | bd.x) <= p) lo = mid; else hi = mid - 1;
+		bool v = false, c = false;
+		if (p < n_scan) {
+			const uint64_t wv = window_at(I.seq, p, I.k);
+			const uint64_t rc = rc64(wv, I.k);
+			const uint64_t x = wv < rc ? wv : rc;
+			const uint32_t mnx = minimizer_of_kmer(x, I.k, I.m);
+			int64_t id = -1;
+			uint32_t own = 0xFFFFFFFFu;
+			if (p < total_nuc) {
+				// last bucket whose start is <= p: the non-empty bucket holding p (empty ones share their successor's start)
+				uint64_t lo = 0, hi = n_buckets - 1;
+				while (lo < hi) {
+					const uint64_t mid = (lo + hi + 1) >> 1;
+					const uint4 bd = __ldg(I.bucket + mid);
+					if ((((uint64_t)bd.y << 32) | bd.x) <= p) lo = mid; else hi = mid - 1;
+				}
+				const uint4 bd = __ldg(I.bucket + lo);
+				const uint64_t start = ((uint64_t)bd.y << 32) | bd.x;
+				if (p >= start && p - start < bd.z) {
+					own = (uint32_t)lo;
+					uint64_t T = ~0ull;
+					id = lookup_one<SMALL>(I, x, own, &T);
+					v = id >= 0;
+					c = v && mnx == own && T == p;
+				}
+				if (pos_id) pos_id[p] = v ? (uint32_t)((uint64_t)id - I.id_base) : 0xFFFFFFFFu;
 			}
-			const uint4 bd = __ldg(I.bucket + lo);
-			const uint64_t start = ((uint64_t)bd.y << 32) | bd.x;
-			if (p >= start && p - start < bd.z) {
-				const uint64_t wv = window_at(I.seq, p, I.k);
-				const uint64_t rc = rc64(wv, I.k);
-				const uint64_t x = wv < rc ? wv : rc;
-				id = lookup_one<SMALL>(I, x, (uint32_t)lo, nullptr, pos_rw);
-				v = id >= 0;
-				if (v && filter) filter_insert(filter, filter_blocks, x);
+			if (filter) {
+				const bool found = mnx == own ? v : lookup_one<SMALL>(I, x, mnx) >= 0;
+				if (found) filter_insert(filter, filter_blocks, x);
 			}
-			if (pos_id) pos_id[p] = v ? (uint32_t)id : 0xFFFFFFFFu;
 		}
-		const uint32_t word = __ballot_sync(0xffffffffu, v);
-		if ((threadIdx.x & 31) == 0) valid[p >> 5] = word;
+		const uint32_t vw = __ballot_sync(0xffffffffu, v);
+		const uint32_t cw = __ballot_sync(0xffffffffu, c);
+		if ((threadIdx.x & 31) == 0 && p < ((total_nuc + 31) & ~31ull)) {
+			valid[p >> 5] = vw;
+			if (cand) cand[p >> 5] = cw;
+		}
+	}
+}
+
+// where the position field of local identifier `lid` lives: group by binary search over the id offsets
+struct FieldRef { uint32_t* word; uint32_t shift, nbits; };
+__device__ __forceinline__ FieldRef field_of(const DevIndexView& I, uint32_t* pos_rw, uint32_t n_groups, uint64_t gid) {
+	uint32_t lo = 0, hi = n_groups - 1;
+	while (lo < hi) {  // last present group whose id_offset <= gid (absent groups repeat their successor's offset and hold no key)
+		const uint32_t mid = (lo + hi + 1) >> 1;
+		if (I.mphf[mid].id_offset <= gid) lo = mid; else hi = mid - 1;
+	}
+	while (!I.mphf[lo].present && lo > 0) lo--;
+	const DevMphf& M = I.mphf[lo];
+	const uint32_t rank = (uint32_t)(gid - M.id_offset);
+	const uint32_t psec = rank / M.fields_per_sector, slot = rank - psec * M.fields_per_sector;
+	const uint32_t o = slot * M.nbits;
+	return FieldRef{pos_rw + ((M.pos_sector_base + psec) << 3) + (o >> 5), o & 31, M.nbits};
+}
+
+// key of a candidate window: (no candidate neighbour) << 8 | offset inside its 2^b windows
+__device__ __forceinline__ uint32_t claim_key(const DevIndexView& I, const uint32_t* __restrict__ cand, uint64_t p, uint64_t total_nuc) {
+	const bool left = p > 0 && ((cand[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u);
+	const bool right = p + 1 < total_nuc && ((cand[(p + 1) >> 5] >> ((p + 1) & 31)) & 1u);
+	return (left || right) ? 0u : 0x100u;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kThreads) k_claim_low(DevIndexView I, uint64_t n_buckets, uint64_t total_nuc, const uint32_t* __restrict__ cand,
+                                                        const uint32_t* __restrict__ pos_id, uint32_t* __restrict__ claim, uint32_t* pos_rw,
+                                                        uint32_t n_groups) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total_nuc; p += stride) {
+		if (!((cand[p >> 5] >> (p & 31)) & 1u)) continue;
+		uint64_t lo = 0, hi = n_buckets - 1;
+		while (lo < hi) {
+			const uint64_t mid = (lo + hi + 1) >> 1;
+			const uint4 bd = __ldg(I.bucket + mid);
+			if ((((uint64_t)bd.y << 32) | bd.x) <= p) lo = mid; else hi = mid - 1;
+		}
+		const uint4 bd = __ldg(I.bucket + lo);
+		const uint64_t start = ((uint64_t)bd.y << 32) | bd.x;
+		const uint32_t j = (uint32_t)(p - start) & ((1u << I.b) - 1u);  // the field's window range starts at a multiple of 2^b
+		const uint32_t key = claim_key(I, cand, p, total_nuc) | j;
+		const uint32_t lid = pos_id[p];
+		if (!WRITE) {
+			atomicMin(claim + lid, key);
+		} else if (j && claim[lid] == key) {
+			const FieldRef f = field_of(I, pos_rw, n_groups, (uint64_t)lid + I.id_base);
+			atomicOr(f.word, j << f.shift);
+			if (f.shift + I.b > 32) atomicOr(f.word + 1, j >> (32 - f.shift));
+		}
 	}
 }
 
@@ -334,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
 								const uint64_t Ta = s_run_T[wid][id];
 								const uint32_t pid = __ldg(I.pos_id + ((s_run_flag[wid][id] & 2) ? Ta + d : Ta - d));
 								v = pid != 0xFFFFFFFFu;
-								emit<MODE>(K, v ? (int64_t)pid : -1, kSlot ? s_run_o[ow][id] + d : 0);
+								emit<MODE>(K, v ? (int64_t)(pid + I.id_base) : -1, kSlot ? s_run_o[ow][id] + d : 0);
 							} else {
 								v = (okv >> (32 + d)) & 1;
 							}
@@ -518,15 +600,30 @@ void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d
 
 const char* g_last_cuda_error = "";
 
-int launch_window_valid(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, uint32_t* d_pos_id,
-                        uint32_t* d_filter, uint32_t filter_blocks, uint32_t* d_pos_rw, cudaStream_t stream) {
+int launch_window_answers(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, uint32_t* d_lid, uint32_t* d_cand,
+                          uint32_t* d_filter, uint32_t filter_blocks, cudaStream_t stream) {
+	if (total_nuc == 0) return 0;
+	const uint64_t n_scan = total_nuc + (1ull << I.b);
+	const uint64_t want = (n_scan + kThreads - 1) / kThreads;
+	const uint64_t cap = (uint64_t)sm_count() * 8;
+	const unsigned grid = (unsigned)(want < cap ? want : cap);
+	if (I.small) k_window_answers<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, n_scan, d_valid, d_lid, d_cand, d_filter, filter_blocks);
+	else k_window_answers<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, n_scan, d_valid, d_lid, d_cand, d_filter, filter_blocks);
+	g_launches++;
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) g_last_cuda_error = cudaGetErrorString(e);
+	return check(e);
+}
+
+int launch_exact_positions(const DevIndexView& I, uint64_t n_buckets, uint64_t n_groups, uint64_t total_nuc, const uint32_t* d_cand,
+                           const uint32_t* d_lid, uint32_t* d_claim, uint32_t* d_pos_rw, cudaStream_t stream) {
 	if (total_nuc == 0) return 0;
 	const uint64_t want = (total_nuc + kThreads - 1) / kThreads;
 	const uint64_t cap = (uint64_t)sm_count() * 8;
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
-	if (I.small) k_window_valid<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks, d_pos_rw);
-	else k_window_valid<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_valid, d_pos_id, d_filter, filter_blocks, d_pos_rw);
-	g_launches++;
+	k_claim_low<false><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_cand, d_lid, d_claim, d_pos_rw, (uint32_t)n_groups);
+	k_claim_low<true><<<grid, kThreads, 0, stream>>>(I, n_buckets, total_nuc, d_cand, d_lid, d_claim, d_pos_rw, (uint32_t)n_groups);
+	g_launches += 2;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) g_last_cuda_error = cudaGetErrorString(e);
 	return check(e);

@@ -13,12 +13,15 @@ namespace blight {
 extern std::atomic<uint64_t> g_launches;
 extern const char* g_last_cuda_error;
 
-// Fills the per-position "window is answered found" bitmap of an uploaded index (see device_index.hpp).
-// d_pos_id / d_filter may be null: the per-position identifier table and the negative filter are filled by the same pass.
-// d_pos_rw: the position sectors, writable, when I.flags has kFlagExactPos (the pass ORs the low b bits of every key's
-// window into its field), else null.
-int launch_window_valid(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, uint32_t* d_pos_id,
-                        uint32_t* d_filter, uint32_t filter_blocks, uint32_t* d_pos_rw, cudaStream_t stream);
+// Upload-time pass over every window of the index text (kernels.cu: k_window_answers): the per-position "answered found"
+// bitmap d_valid, the per-position local identifier d_lid (id - I.id_base, 0xFFFFFFFF = -1; may be null), the candidate
+// bitmap d_cand of the exact-position layout (may be null) and the negative filter d_filter (may be null).
+int launch_window_answers(const DevIndexView& I, uint64_t n_buckets, uint64_t total_nuc, uint32_t* d_valid, uint32_t* d_lid, uint32_t* d_cand,
+                          uint32_t* d_filter, uint32_t filter_blocks, cudaStream_t stream);
+// Exact-position layout: one candidate window per position field (d_claim: one u32 per local identifier, preset to
+// 0xFFFFFFFF) ORs where it sits inside its 2^b windows into the field's low b bits (d_pos_rw = the position sectors).
+int launch_exact_positions(const DevIndexView& I, uint64_t n_buckets, uint64_t n_groups, uint64_t total_nuc, const uint32_t* d_cand,
+                           const uint32_t* d_lid, uint32_t* d_claim, uint32_t* d_pos_rw, cudaStream_t stream);
 
 // ids[i] = lookup(canon[i]); d_mini may be null (the minimizer is then computed from the k-mer).
 int launch_lookup_kmers(const DevIndexView& I, const uint64_t* d_canon, const uint32_t* d_mini, uint64_t n, int64_t* d_ids,

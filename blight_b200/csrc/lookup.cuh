@@ -237,7 +237,7 @@ static __device__ __noinline__ bool fallback_rank(const DevIndexView& I, const u
 // Everything after the level probe: rank (or fallback map), position, guard, window scan, id.
 // T_out receives the absolute base position of the window that matched (when the result is >= 0).
 __device__ __forceinline__ int64_t finish_lookup(const DevIndexView& I, const BucketRef& B, uint64_t x, bool hit,
-                                                 const uint32_t (&w)[8], uint32_t r, uint64_t* T_out = nullptr, uint32_t* pos_rw = nullptr) {
+                                                 const uint32_t (&w)[8], uint32_t r, uint64_t* T_out = nullptr) {
 	const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(B.M) + 1);  // id_offset, fb_off
 	const uint4 m2 = __ldg(reinterpret_cast<const uint4*>(B.M) + 2);  // fb_count, nbits, fields_per_sector, fps_magic
 	uint32_t rank;
@@ -268,14 +268,6 @@ __device__ __forceinline__ int64_t finish_lookup(const DevIndexView& I, const Bu
 	const int32_t j = (I.k >= 8 && I.b >= 3) ? scan_windows(I.seq, P, I.k, 1u << I.b, x, rx) : scan_windows_loop(I.seq, P, I.k, 1u << I.b, x, rx);
 	if (j < 0) return -1;
 	if (T_out) *T_out = P + (uint32_t)j;
-	if (pos_rw && exact && j) {
-		// upload pass (k_window_valid): remember where inside its 2^b windows this key sits. Low bits start at zero and every
-		// writer of a field writes the same value, so two atomic ORs (the field may straddle two words) are enough; a lookup
-		// that reads a half-written field just takes the scan above.
-		uint32_t* wp = pos_rw + (ps - I.pos);
-		atomicOr(wp + ow, (uint32_t)j << (o & 31));
-		if ((o & 31) + I.b > 32) atomicOr(wp + ow + 1, (uint32_t)j >> (32 - (o & 31)));
-	}
 	return (int64_t)id;
 }
 
@@ -312,14 +304,14 @@ __device__ __forceinline__ void filter_insert(uint32_t* filter, uint32_t filter_
 }
 
 template <bool SMALL>
-__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini, uint64_t* T_out = nullptr, uint32_t* pos_rw = nullptr) {
+__device__ __forceinline__ int64_t lookup_one(const DevIndexView& I, uint64_t x, uint32_t mini, uint64_t* T_out = nullptr) {
 	const BucketRef B = load_bucket(I, mini);
 	if (B.bd.z == 0) return -1;
 	uint64_t s0 = 0, s1 = 0, off = 0;
 	uint32_t w[8];
 	uint32_t r = 0;
 	const bool hit = probe_levels<SMALL>(B, x, 0, kLevels, s0, s1, off, w, r);
-	return finish_lookup(I, B, x, hit, w, r, T_out, pos_rw);
+	return finish_lookup(I, B, x, hit, w, r, T_out);
 }
 
 }  // namespace blight

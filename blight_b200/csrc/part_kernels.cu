@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 					uint64_t T = 0;
 					const int64_t idr = lookup_one<SMALL>(I, f < rc ? f : rc, mn, &T);
 					if (idr >= 0) found++; else notfound++;
-					if (WANT_IDS) s_ids[iw][i] = (uint32_t)idr;  // -1 -> kIdAbsent; ids < 2^32 - 1 (the table exists)
+					if (WANT_IDS) s_ids[iw][i] = idr >= 0 ? (uint32_t)((uint64_t)idr - I.id_base) : kIdAbsent;  // slice-local: fits 32 bits (the table exists)
 					if (d == 0) {
 						uint32_t flag = 0, dmax = 0;
 						if (idr >= 0) {
@@ -444,8 +444,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 
 // Source side, after the owners answered: return streams -> int64 ids in read order. A warp takes 32 consecutive
 // records of one owner from the side table; their ids are consecutive in that owner's return region.
+struct IdBases { uint64_t v[kMaxRanks]; };  // first identifier of every owner's slice: owners return slice-local 32-bit ids
+
 __global__ void __launch_bounds__(kThreads) k_scatter_runs(const uint4* __restrict__ side, uint64_t cap, const unsigned long long* __restrict__ counts,
-                                                           const uint32_t* __restrict__ ret, uint64_t kcap, uint32_t world,
+                                                           const uint32_t* __restrict__ ret, uint64_t kcap, uint32_t world, IdBases bases,
                                                            int64_t* __restrict__ out) {
 	__shared__ unsigned long long s_pref[kMaxRanks + 1];
 	__shared__ unsigned long long s_cnt[kMaxRanks];
@@ -489,11 +491,12 @@ __global__ void __launch_bounds__(kThreads) k_scatter_runs(const uint4* __restri
 		const uint32_t ko0 = __shfl_sync(0xffffffffu, ko, 0);
 		__syncwarp();
 		const uint32_t* srcp = ret + (uint64_t)d * kcap + ko0;
+		const long long id0 = (long long)bases.v[d];
 		for (uint32_t i = lane; i < n_ids; i += 32) {
 			const uint32_t run = run_of(s_incl[wid], i);
 			const uint32_t dd = i - (run ? s_incl[wid][run - 1] : 0u);
 			const uint32_t v = __ldcs(srcp + i);
-			__stcs(reinterpret_cast<long long*>(out + s_o[wid][run] + dd), v == kIdAbsent ? -1ll : (long long)v);
+			__stcs(reinterpret_cast<long long*>(out + s_o[wid][run] + dd), v == kIdAbsent ? -1ll : id0 + (long long)v);
 		}
 	}
 }
@@ -604,13 +607,15 @@ int blight_part_lookup(const blight_index* idx, uint32_t world, const void* cons
 }
 
 int blight_part_scatter(const void* d_side, uint64_t cap, const uint64_t* d_counts, const void* d_ret, uint64_t kcap, uint32_t world,
-                        uint64_t max_records, int64_t* d_ids, void* stream) {
+                        uint64_t max_records, const uint64_t* id_bases, int64_t* d_ids, void* stream) {
 	if (!d_side || !d_counts || !d_ret || !d_ids) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (world == 0 || world > (uint32_t)kMaxRanks) return fail(BL_ERR_INVALID_ARG, "bad world");
 	const uint64_t want = std::max<uint64_t>(1, ((max_records + 31) / 32 + world + kWarps - 1) / kWarps);
 	const uint64_t capb = (uint64_t)sm_count_() * 8;
+	IdBases bases{};
+	if (id_bases) for (uint32_t i = 0; i < world; i++) bases.v[i] = id_bases[i];
 	k_scatter_runs<<<(unsigned)(want < capb ? want : capb), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-		static_cast<const uint4*>(d_side), cap, reinterpret_cast<const unsigned long long*>(d_counts), static_cast<const uint32_t*>(d_ret), kcap, world, d_ids);
+		static_cast<const uint4*>(d_side), cap, reinterpret_cast<const unsigned long long*>(d_counts), static_cast<const uint32_t*>(d_ret), kcap, world, bases, d_ids);
 	g_launches++;
 	return finish("k_scatter_runs");
 }

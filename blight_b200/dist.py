@@ -281,6 +281,13 @@ class PartitionedSet:
         self._counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
         self._recv_counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        # owners return slice-local 32-bit ids; the scatter adds the owner's first identifier back
+        bases = [None] * world
+        if world > 1:
+            dist.all_gather_object(bases, int(self.index.info["id_base"]), group=self.group)
+        else:
+            bases = [int(self.index.info["id_base"])]
+        self._id_bases = np.asarray(bases, dtype=np.uint64)
         self._side_stream = torch.cuda.Stream(device=dev)
         self._ev_pub = torch.cuda.Event()
         self._ev_scat = [torch.cuda.Event(), torch.cuda.Event()]
@@ -325,7 +332,7 @@ class PartitionedSet:
             # on a second stream, next to the lookup of the following sub-batch (it only moves bytes)
             self._ev_pub.record(main)
             side.wait_event(self._ev_pub)
-            api.part_scatter(self._side_at[b], self._cap, self._counts[b], self._ret_mine[b], self._kcap, world, max_rec, ids, stream=side)
+            api.part_scatter(self._side_at[b], self._cap, self._counts[b], self._ret_mine[b], self._kcap, world, max_rec, ids, self._id_bases, stream=side)
             self._ev_scat[b].record(side)
 
         pending = [False, False]

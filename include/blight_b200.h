@@ -45,7 +45,7 @@ typedef struct blight_index blight_index; /* device-resident index */
 
 typedef struct blight_info {
 	uint32_t k, m, n_log2, s_log2, b;
-	uint32_t reserved;
+	uint32_t layout;            /* blight_index only: BLIGHT_LAYOUT_* bits of the derived tables actually resident */
 	uint64_t n_buckets;         /* 2^(2m-1), blight.h:70 */
 	uint64_t n_mphf;            /* 2^n, blight.h:68 */
 	uint64_t number_kmer;       /* kmer_Set_Light::number_kmer, blight.h:52 */
@@ -57,6 +57,7 @@ typedef struct blight_info {
 	uint64_t largest_mphf;      /* kmer_Set_Light::largest_MPHF, blight.h:54 */
 	uint64_t largest_bucket;    /* kmer_Set_Light::largest_bucket_nuc_all, blight.h:59 */
 	uint64_t device_bytes;      /* HBM bytes held by a blight_index (0 for a blight_flat) */
+	uint64_t id_base;           /* smallest identifier this index can return: 0 for a whole index, the slice's first for blight_flat_slice */
 } blight_info;
 
 const char* blight_version(void);
@@ -93,8 +94,23 @@ int blight_flat_group_sizes(const blight_flat* f, uint64_t* sizes_out);
 
 /* ---- device side ------------------------------------------------------------------------------------ */
 
-/* Re-lays the flat image out for the GPU and uploads it to `device`. */
+/* Re-lays the flat image out for the GPU and uploads it to `device`, with the default (fastest) set of derived tables. */
 int blight_index_upload(const blight_flat* f, int device, blight_index** out);
+
+/* The HBM footprint is a choice: the reference's own arrays re-laid out cost ~28 bits per k-mer; the
+ * derived tables that make the read kernels 2.5x faster cost ~130 more. Each field: 1 = on, 0 = off, -1 = library default. */
+#define BLIGHT_LAYOUT_POS_ID 1u    /* position -> identifier table: 32 bits per base of index text (~106 bits per k-mer) */
+#define BLIGHT_LAYOUT_FILTER 2u    /* negative filter: filter_bits per k-mer */
+#define BLIGHT_LAYOUT_EXACT_POS 4u /* position fields widened by b bits: the 2^b-window scan becomes one window */
+typedef struct blight_upload_options {
+	uint32_t struct_size;   /* = sizeof(blight_upload_options) */
+	int32_t pos_id;         /* default 1 (dropped by itself when the index or slice holds 2^32-1 k-mers or more, or HBM is short) */
+	int32_t filter_bits;    /* bits per k-mer, 0 = no filter; default 20 */
+	int32_t exact_pos;      /* default 1 */
+	int32_t filter_anchors; /* first k-mers of super-k-mers go through the filter too; default 1 */
+} blight_upload_options;
+/* opts == NULL: all defaults. "Compact" = {sizeof, 0, 0, 0, 0}: only the reference's arrays (+1 bit per base). */
+int blight_index_upload_opts(const blight_flat* f, int device, const blight_upload_options* opts, blight_index** out);
 void blight_index_free(blight_index* idx);
 int blight_index_info(const blight_index* idx, blight_info* out);
 
@@ -201,9 +217,10 @@ int blight_part_lookup(const blight_index* idx, uint32_t world, const void* cons
                        void* const* ret, uint64_t cap, uint64_t kcap, uint64_t* d_ctr, void* stream);
 /* Back on the source, once every owner has answered: return regions (d_ret: world regions of kcap 32-bit ids, region d
  * written by owner d) -> int64 ids at the slots query_sequence_hash would fill (blight.cpp:575-591), through the side
- * table and the counters the dispatch left. */
+ * table and the counters the dispatch left. Owners return slice-local 32-bit ids: id_bases[d] (HOST array, world entries,
+ * blight_info.id_base of owner d's index; NULL = all zero) is added back here. */
 int blight_part_scatter(const void* d_side, uint64_t cap, const uint64_t* d_counts, const void* d_ret, uint64_t kcap, uint32_t world,
-                        uint64_t max_records, int64_t* d_ids, void* stream);
+                        uint64_t max_records, const uint64_t* id_bases, int64_t* d_ids, void* stream);
 /* Device buffers other processes of the box can map (CUDA IPC): alloc + 64-byte handle here, open there. */
 int blight_peer_alloc(uint64_t bytes, void** d_ptr, unsigned char* handle64);
 int blight_peer_open(const unsigned char* handle64, void** d_ptr);

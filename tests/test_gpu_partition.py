@@ -137,8 +137,10 @@ def test_three_owners_two_sources_on_one_gpu(tmp_path, torch_cuda):
         assert int(cnt_d[2]) == 0 and int(cnt_d[0]) > 0
         ret_ptrs = [ret[s, d].data_ptr() for s in range(2)] + [0]
         api.part_lookup(owners[d], regions, cnt_d, ret_ptrs, cap, kcap, ctr)
+    bases = np.asarray([o.info["id_base"] for o in owners], dtype=np.uint64)
+    assert bases[0] == 0 and bases[1] > 0 and bases[2] > bases[1]  # owners answer with slice-local 32-bit ids
     for s in range(2):
-        api.part_scatter(side[s].data_ptr(), cap, counts[s], ret[s].data_ptr(), kcap, world, world * cap, ids_bufs[s])
+        api.part_scatter(side[s].data_ptr(), cap, counts[s], ret[s].data_ptr(), kcap, world, world * cap, ids_bufs[s], bases)
     torch.cuda.synchronize()
     for s in range(2):
         assert np.array_equal(ids_bufs[s].cpu().numpy(), parts[s][2]), s

@@ -98,3 +98,35 @@ def test_reference_import_roundtrip(tmp_path):
     ref = oracle.Reference.from_blob(blob, 31, 7)
     ids, f, nf, _ = ref.query_reads(bases, offs, threads=1)
     assert fixtures.digest(ids) == ANS["lambda"]["m7_n5_s3_b6"]["sha256"]
+
+
+def test_bucket_end_shapes_hold_bucket_end_keys(tmp_path):
+    """The adversarial shapes of tests/test_gpu_index_text.py do contain keys the reference answers only through a window
+    no own-bucket lookup answers; the C port returns the known identifiers for the first shape."""
+    for i, shape in enumerate(common.BUCKET_END_SHAPES):
+        flat, text, port, holes = common.bucket_end_case(shape, str(tmp_path))
+        assert len(holes) > 0, shape
+        if i == 0:
+            assert {hex(k): v for k, v in holes} == common.KNOWN_BUCKET_END_IDS
+
+
+@pytest.mark.skipif(not oracle.reference_available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("shape", common.BUCKET_END_SHAPES[:2])
+def test_bucket_end_keys_against_live_reference(shape, tmp_path):
+    """The index text as one read, through the reference's own construct_index + query_sequence_hash: same ids as the C
+    port on our builder's blob, including the keys found through a window past their bucket's end (blight.cpp:729-740)."""
+    G, gs, um, us, k, m, n, b = shape
+    flat, text, port, holes = common.bucket_end_case(shape, str(tmp_path))
+    g = synth.random_genome(G, seed=gs)
+    st, ln = synth.cut_unitigs(g, k, um, seed=us)
+    ub, uo = synth.concat_sequences(g, st, ln)
+    fa = os.path.join(str(tmp_path), "u.fa")
+    open(fa, "wb").write(synth.fasta_bytes(ub, uo))
+    ref = oracle.Reference(k, m, n, 0, 1, b)
+    ref.construct_index(fa)
+    off = np.array([0, len(text)], dtype=np.uint64)
+    rids, f, nf, _ = ref.query_reads(text, off, threads=1)
+    pids, ctr = port.query_reads(text, off)
+    assert np.array_equal(rids, pids) and f == int(ctr[0])
+    hk = np.array([h[0] for h in holes], dtype=np.uint64)
+    assert [int(v) for v in ref.query_kmers(hk)] == [h[1] for h in holes]
