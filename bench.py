@@ -8,13 +8,19 @@ Workload (BASELINE.json configs[2]/[3], the one the north-star target is quoted 
 unitig graph with 100 M 31-mers, index k=31 m=7 n=5 s=3 b=6, replicated on every GPU; each GPU queries its own
 10 M simulated 150 bp reads (1 % substitutions, half reverse-complemented) = 1.2 G k-mers per step per GPU
 (weak scaling, no data-path collective).  A step is one pass of the hot path (read tiles -> 2-bit pack -> rolling
-canonical k-mers + minimizers -> MPHF -> positions -> 2^b-window compare -> int64 ids) over that batch.
+canonical k-mers + minimizers -> MPHF -> positions -> 2^b-window compare -> counters / int64 ids) over that batch.
 
-  value      k-mers/s, all GPUs, inputs resident in HBM, CUDA events, max over ranks
-  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D of the reads + kernels + D2H of the
-             counters inside the timed region (file_query semantics: Good / Erroneous counts)
-  roofline   algorithmic bytes per k-mer (158 B for b<=6) x k-mers / kernel time vs measured HBM peak
-  cpu_baseline   the reference's own query code (oracle/_ref) on the host cores, on a bounded sample of the reads
+  value           k-mers/s, all GPUs, inputs resident in HBM, CUDA events, max over ranks
+  e2e             same metric through the C ABI with HOST (pinned) buffers: H2D of the reads + kernels + D2H of the
+                  counters inside the timed region (file_query semantics: Good / Erroneous counts); bytes counted by the
+                  library from the copies it actually issued
+  file_query      kmer_Set_Light::file_query(path) end to end from a 2-line FASTA file (N = 1)
+  roofline        algorithmic bytes per k-mer x k-mers / kernel time vs measured HBM peak
+  cpu_baseline    the reference's own query code (oracle/_ref) on the host cores, on a bounded sample of the reads:
+                  the in-memory OpenMP loop and the reference's own file_query -t $(nproc)
+  partition_mode  (N > 1) BASELINE configs[4] shape: a 1 G-k-mer index (k31 m9 n10 b6) cut by minimizer bucket over the N
+                  GPUs, super-k-mers and ids exchanged as peer-memory stores inside the kernels; k-mers/s with ids and
+                  counting, ratio to ONE GPU holding the whole index, ids compared with that GPU's in the run
 """
 from __future__ import annotations
 
@@ -50,11 +56,16 @@ def parse():
     ap.add_argument("--cpu-sample-reads", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-file-query", action="store_true")
     ap.add_argument("--ids-only", action="store_true", help="diagnostic: time only the id (hash) mode")
     ap.add_argument("--count-only", action="store_true", help="diagnostic: time only the counting (bool) mode")
-    ap.add_argument("--partition", action="store_true",
-                    help="N > 1: minimizer-bucket partitioned index (BASELINE configs[4]) instead of a replica per GPU; the "
-                         "exchange is fused into the kernels (peer-memory stores over NVLink)")
+    ap.add_argument("--compact", action="store_true", help="diagnostic: upload without the derived tables (the reference's arrays only)")
+    ap.add_argument("--no-partition", action="store_true", help="N > 1: skip the bucket-partitioned leg")
+    ap.add_argument("--partition-genome", type=int, default=1_000_000_000)
+    ap.add_argument("--partition-reads", type=int, default=4_000_000, help="reads per GPU per batch of the partitioned leg")
+    ap.add_argument("--partition-shape", default="9,10,6", help="m,n,b of the partitioned index")
+    ap.add_argument("--partition-sub", type=int, default=32 << 20, help="base positions per sub-batch of the partitioned leg")
+    ap.add_argument("--build-blob", default=None, help=argparse.SUPPRESS)  # internal: build the workload index, save it, exit
     return ap.parse_args()
 
 
@@ -128,8 +139,40 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(local: int):
+    """Runs this process (and hence first-touches its pinned buffers) on the cores NVML lists as local to its GPU: with 8
+    ranks on a two-socket box, host buffers on the far socket cost every H2D copy a trip over the socket link."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
+def build_flat(args):
+    """The workload's index, built by the product's host builder from the seeded synthetic unitigs."""
+    from blight_b200 import api, synth
+    g = synth.random_genome(args.genome, seed=42)
+    st, ln = synth.cut_unitigs(g, args.k, 2000, seed=43)
+    # torchrun exports OMP_NUM_THREADS=1: ask for the host's cores explicitly
+    return g, api.FlatIndex.build_spans(g, st, ln, args.k, args.m, args.n, args.s, args.b, threads=os.cpu_count() or 1)
+
+
 def build_workload_index(args, rank, world, tmpdir):
-    """Rank 0 builds the flat index with the product's host builder and saves it; the others load the blob."""
+    """Rank 0 builds the flat index and saves it; the others load the blob."""
     from blight_b200 import api, synth
     if world > 1:
         import torch.distributed as dist
@@ -137,13 +180,12 @@ def build_workload_index(args, rank, world, tmpdir):
         dist.broadcast_object_list(box, src=0)  # every rank must look in rank 0's directory
         tmpdir = box[0]
     blob = os.path.join(tmpdir, "bench_index.blflat")
-    g = synth.random_genome(args.genome, seed=42)
     t0 = time.time()
     if rank == 0:
-        st, ln = synth.cut_unitigs(g, args.k, 2000, seed=43)
-        # torchrun exports OMP_NUM_THREADS=1: ask for the host's cores explicitly
-        flat = api.FlatIndex.build_spans(g, st, ln, args.k, args.m, args.n, args.s, args.b, threads=os.cpu_count() or 1)
+        g, flat = build_flat(args)
         flat.save(blob)
+    else:
+        g = synth.random_genome(args.genome, seed=42)
     if world > 1:
         dist.barrier()
         if rank != 0:
@@ -151,20 +193,74 @@ def build_workload_index(args, rank, world, tmpdir):
     return g, flat, blob, time.time() - t0
 
 
+def fasta_of(reads_2d: np.ndarray) -> np.ndarray:
+    """2-line FASTA text of fixed-length reads: '>\\n' + bases + '\\n' per read (the reference skips the header line
+    whatever it holds, blight.cpp:760-772)."""
+    n, L = reads_2d.shape
+    rec = np.empty((n, L + 3), dtype=np.uint8)
+    rec[:, 0] = ord(">")
+    rec[:, 1] = ord("\n")
+    rec[:, 2:2 + L] = reads_2d
+    rec[:, -1] = ord("\n")
+    return rec.reshape(-1)
+
+
+def shm_dir():
+    return "/dev/shm" if os.path.isdir("/dev/shm") else None
+
+
+def reference_measure(blob, k, m, sample_bases: np.ndarray, n_s: int, read_len: int, warm: bool = True):
+    """The reference's own code on the host cores, on n_s reads: (in-memory OpenMP loop over query_sequence_bool,
+    the reference's own file_query -t cores). Returns dicts."""
+    import oracle
+    kpr = read_len - k + 1
+    so = np.arange(n_s + 1, dtype=np.uint64) * np.uint64(read_len)
+    threads = os.cpu_count() or 1
+    ref = oracle.Reference.from_blob(blob, k, m, cores=threads)  # file_query uses the object's core count (blight.h:18)
+    if warm:
+        ref.query_reads(sample_bases[: 2000 * read_len], so[:2001], threads=threads, want_ids=False)
+    _, f, nf, sec = ref.query_reads(sample_bases, so, threads=threads, want_ids=False)
+    mem = {"value": n_s * kpr / sec, "unit": "k-mers/s", "cores": threads, "kind": "reference", "seconds": sec, "found": f, "not_found": nf,
+           "sample": f"first {n_s} reads of the step ({n_s * kpr} k-mers), in-memory OpenMP loop over query_sequence_bool, {sec:.2f} s"}
+    fq = None
+    try:
+        d = tempfile.mkdtemp(prefix="blight_ref_fq_", dir=shm_dir())
+        path = os.path.join(d, "sample.fa")
+        fasta_of(sample_bases.reshape(n_s, read_len)).tofile(path)
+        q0 = int(ref.L.blref_number_query(ref.h))
+        t0 = time.perf_counter()
+        rc = ref.file_query(path)
+        dt = time.perf_counter() - t0
+        done = int(ref.L.blref_number_query(ref.h)) - q0
+        os.remove(path)
+        os.rmdir(d)
+        if rc == 0 and done > 0:
+            fq = {"value": done / dt, "unit": "k-mers/s", "cores": threads, "seconds": dt,
+                  "sample": f"kmer_Set_Light::file_query on a FASTA file of the same {n_s} reads (tmpfs), -t {threads}, wall clock around the call (file reading included, blight.cpp:746-799)"}
+    except Exception as ex:  # reported, never required
+        fq = {"value": None, "error": repr(ex)}
+    return mem, fq
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU query code (oracle/_ref: /root/reference + fixes P1/P2, compiled by
-    oracle/build_ref.sh) on the host cores, all threads, on a bounded sample of the same workload per step."""
+    oracle/build_ref.sh) on the host cores, all threads, on a bounded sample of the same workload per step. This process
+    never maps the product library: the index blob is built by a child process and imported into the reference object."""
     if rank != 0:
         return
     import oracle
-    from blight_b200 import api, synth
+    from blight_b200 import synth
     if not oracle.reference_available():
         emit({"impl": "reference", "unavailable": "oracle/_ref/libblight_ref.so was not built (needs /root/reference at build time)"})
         return
-    with tempfile.TemporaryDirectory() as td:
-        g, flat, blob, _ = build_workload_index(args, 0, 1, td)
-        ref = oracle.Reference.from_blob(blob, args.k, args.m)  # reference object holding the identical index
-    threads = os.cpu_count() or ref.max_threads()
+    td = tempfile.mkdtemp(prefix="blight_refarm_", dir=shm_dir())
+    blob = os.path.join(td, "bench_index.blflat")
+    cmd = [sys.executable, os.path.abspath(__file__), "--build-blob", blob, "--genome", str(args.genome), "--k", str(args.k), "--m", str(args.m),
+           "--n", str(args.n), "--s", str(args.s), "--b", str(args.b)]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    g = synth.random_genome(args.genome, seed=42)
+    threads = os.cpu_count() or 1
+    ref = oracle.Reference.from_blob(blob, args.k, args.m, cores=threads)
     n_reads = args.cpu_sample_reads
     rb, ro = synth.simulate_reads(g, n_reads, args.read_len, 0.01, 0.5, seed=44)
     kmers = n_reads * (args.read_len - args.k + 1)
@@ -175,15 +271,20 @@ def run_reference(args, rank):
         _, f, nf, sec = ref.query_reads(rb, ro, threads=threads, want_ids=False)
         t += sec
     val = kmers * args.steps / t
+    _, fq = reference_measure(blob, args.k, args.m, rb, n_reads, args.read_len, warm=False)
+    os.remove(blob)
+    os.rmdir(td)
+    mapped = [ln.split()[-1] for ln in open("/proc/self/maps") if "libblight_b200" in ln]
     line = {
         "impl": "reference", "metric": "queried k-mers/s", "value": val, "unit": "k-mers/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args, 1) | {"sample": f"{n_reads} reads ({kmers} k-mers) per step"},
         "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": threads, "kind": "reference",
-                         "sample": f"{n_reads} reads x {args.read_len} bp = {kmers} k-mers per step, in-memory OpenMP loop over query_sequence_bool"},
+                         "sample": f"{n_reads} reads x {args.read_len} bp = {kmers} k-mers per step, in-memory OpenMP loop over query_sequence_bool",
+                         "file_query": fq},
         "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "found": f, "not_found": nf,
+        "found": f, "not_found": nf, "product_library_mapped": bool(mapped),
     }
     emit(line)
 
@@ -194,9 +295,8 @@ def workload_config(args, world):
                     f"{args.reads} simulated {args.read_len} bp reads per GPU per step (1% subst., 50% revcomp), file_query semantics (found / not-found counts; the id mode is reported under ids_mode)",
         "k": args.k, "m": args.m, "n": args.n, "s": args.s, "b": args.b,
         "kmers_per_step_per_gpu": args.reads * (args.read_len - args.k + 1),
-        "parallelism": (f"partition x{world}: MPHF groups sharded, super-k-mers and ids exchanged as peer-memory stores inside the kernels"
-                        if getattr(args, "partition", False) and world > 1 else f"replica x{world}, reads sharded, no data-path collective"),
-        "cache": "inputs (1.5 GB of reads per step) and the index (1.8 GB in HBM) exceed the 126 MB L2; no explicit flush",
+        "parallelism": f"replica x{world}, reads sharded, no data-path collective" + ("; partition_mode: MPHF groups sharded, super-k-mers and ids exchanged as peer-memory stores inside the kernels" if world > 1 else ""),
+        "cache": "inputs (1.5 GB of reads per step) and the index (2 GB in HBM) exceed the 126 MB L2; no explicit flush",
     }
 
 
@@ -216,10 +316,130 @@ def emit(line: dict):
     print(json.dumps(line), file=OUT or sys.stdout, flush=True)
 
 
+def read_kernel_name(info, want_ids, k, m):
+    """The kernel the launcher picks for a mode (kernels.cu: launch_reads_t / use_superkmer_kernel), from the layout in force."""
+    from blight_b200 import api
+    forced = os.environ.get("BLIGHT_READS_KERNEL", "")[:1]
+    sk = k - m + 1 >= 8 and not (want_ids and not (info["layout"] & api.LAYOUT_POS_ID))
+    if sk and forced == "p":
+        sk = False
+    return ("k_reads_sk" if sk else "k_reads") + ("<ids>" if want_ids else "<count>")
+
+
+def partition_leg(args, rank, world, local, dev):
+    """BASELINE configs[4] shape under the driver's own launch: a 1 G-k-mer index cut by minimizer bucket over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from blight_b200 import api, synth
+    from blight_b200 import dist as bdist
+    m, n, b = (int(x) for x in args.partition_shape.split(","))
+    gl, n_reads = args.partition_genome, args.partition_reads
+    try:
+        import psutil
+        avail_gb = psutil.virtual_memory().available / 1e9
+    except Exception:
+        avail_gb = float("inf")
+    need_gb = world * (gl * 5e-9 + 2) + gl * 12e-9
+    if avail_gb < need_gb:
+        return {"skipped": f"needs about {need_gb:.0f} GB of host memory, {avail_gb:.0f} GB available"}
+    t_leg = time.time()
+    wd = [None]
+    if rank == 0:
+        wd = [tempfile.mkdtemp(prefix="blight_part_", dir=shm_dir())]
+    dist.broadcast_object_list(wd, src=0)
+    blob = os.path.join(wd[0], "full.blflat")
+    g = synth.random_genome(gl, seed=42)
+    flat = None
+    t0 = time.time()
+    if rank == 0:
+        st, ln = synth.cut_unitigs(g, args.k, 2000, seed=43)
+        flat = api.FlatIndex.build_spans(g, st, ln, args.k, m, n, 3, b, threads=os.cpu_count() or 1)
+        flat.save(blob)
+    build_s = time.time() - t0
+    part = bdist.PartitionedSet.from_full(flat, local, wd[0])
+    if rank != 0:
+        flat = api.FlatIndex.load(blob)
+    N = flat.info()["number_kmer"]
+    whole = flat.upload(local)  # every rank also holds the whole index: ground truth for its own reads, and the one-GPU rate
+    del flat
+    d_genome = torch.from_numpy(g).to(dev)
+    del g
+    kpr = args.read_len - args.k + 1
+    bases = synth.torch_simulate_reads(d_genome, n_reads, args.read_len, 0.01, 0.5, seed=144 + rank)
+    del d_genome
+    roff = torch.arange(0, n_reads + 1, device=dev, dtype=torch.int64) * args.read_len
+    koff = torch.arange(0, n_reads + 1, device=dev, dtype=torch.int64) * kpr
+    total = n_reads * kpr
+    reps = max(3, min(args.steps, 10))
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ids_one, ctr_one = whole.query_reads(bases, roff, koff, total)
+    torch.cuda.synchronize()
+    ids_one = ids_one[:total]
+    ctr_all = ctr_one.clone()
+    dist.all_reduce(ctr_all)
+    scratch = torch.empty(total, dtype=torch.int64, device=dev)
+    one_ids_ms = timed(lambda: whole.query_reads(bases, roff, koff, total, ids=scratch))
+    one_cnt_ms = timed(lambda: whole.query_reads(bases, roff, want_ids=False))
+    del scratch
+    whole_bytes = whole.info["device_bytes"]
+
+    part.enable_fused(sub_positions=args.partition_sub, ids_capacity=total)
+    ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
+    torch.cuda.synchronize()
+    same = torch.tensor([1 if torch.equal(ids_f, ids_one) else 0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    _, ctr_c = part.query_reads_fused(bases, roff, want_ids=False)
+    torch.cuda.synchronize()
+    ctr_ok = bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]) and torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
+    del ids_one, whole
+    torch.cuda.empty_cache()
+    f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, check_overflow=False))
+    f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False))
+    ovf = torch.tensor([1 if part.overflowed() else 0], device=dev)
+    dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
+    local_bytes = part.index.info["device_bytes"]
+    part.disable_fused()
+    dist.barrier()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(wd[0], ignore_errors=True)
+    return {
+        "workload": f"synthetic {gl / 1e6:g} Mbp random-genome unitig graph ({N} {args.k}-mers), index k={args.k} m={m} n={n} b={b} cut into {world} contiguous "
+                    f"ranges of MPHF groups (one per GPU); every GPU holds {n_reads} reads ({total} k-mers) per batch; CUDA events, max over ranks, {reps} batches",
+        "ids": {"value": world * total / (f_ids_ms * 1e-3), "unit": "k-mers/s", "ms_per_batch": f_ids_ms},
+        "counting": {"value": world * total / (f_cnt_ms * 1e-3), "unit": "k-mers/s", "ms_per_batch": f_cnt_ms},
+        "one_gpu_whole_index": {"ids": total / (one_ids_ms * 1e-3), "counting": total / (one_cnt_ms * 1e-3), "unit": "k-mers/s",
+                                "ids_ms": one_ids_ms, "counting_ms": one_cnt_ms, "device_bytes": whole_bytes},
+        "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms, "counting_vs_one_gpu": world * one_cnt_ms / f_cnt_ms,
+        "ids_equal_replica": bool(same.item()), "counters_equal_replica": ctr_ok, "overflow": bool(ovf.item()),
+        "device_bytes_per_gpu": local_bytes, "cuts": part.plan.cuts, "sub_positions": part._sub,
+        "return_path": os.environ.get("BLIGHT_PART_RETURN", "session") + ("+ahead" if os.environ.get("BLIGHT_PART_ORDER") == "ahead" else ""),
+        "build_seconds": build_s, "leg_seconds": time.time() - t_leg,
+    }
+
+
 def main():
     global OUT
-    OUT = claim_stdout()
     args = parse()
+    if args.build_blob:
+        _, flat = build_flat(args)
+        flat.save(args.build_blob)
+        return
+    OUT = claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -234,21 +454,18 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (blight_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    tmpdir = tempfile.mkdtemp(prefix="blight_bench_")
+    tmpdir = tempfile.mkdtemp(prefix="blight_bench_", dir=shm_dir())
     g, flat, blob, build_s = build_workload_index(args, rank, world, tmpdir)
     info = flat.info()
-    part = None
-    if args.partition and world > 1:
-        from blight_b200 import dist as bdist
-        part = bdist.PartitionedSet.from_full(flat if rank == 0 else None, local, os.path.dirname(blob))
-        part.enable_fused()
-        idx = part.index
-    else:
-        idx = flat.upload(local)
+    t0 = time.time()
+    idx = flat.upload(local, api.UploadOptions.compact() if args.compact else None)
+    torch.cuda.synchronize()
+    upload_s = time.time() - t0
     kpr = args.read_len - args.k + 1
     total_kmers = args.reads * kpr
 
@@ -262,18 +479,10 @@ def main():
     d_ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
 
     def step_count():
-        if part is not None:
-            _, c = part.query_reads_fused(d_bases, d_roff, want_ids=False, check_overflow=False)
-            d_ctr.add_(c // world)  # the fused path returns the counters summed over the ranks
-        else:
-            idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
+        idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
 
     def step_ids():
-        if part is not None:
-            _, c = part.query_reads_fused(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, check_overflow=False)
-            d_ctr.add_(c // world)
-        else:
-            idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
+        idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -318,12 +527,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     found_frac = float(ctr[api.CTR_FOUND]) / max(1.0, float(ctr[api.CTR_QUERIES]))
     value = world * total_kmers * args.steps / (ms * 1e-3)
+    del d_ids
 
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + kernels + D2H inside the timed region ----
-    if part is not None and part.overflowed():
-        raise SystemExit("bench.py --partition: an inbox region overflowed, the timed steps dropped records")
     e2e = None
-    if not args.no_e2e and part is None:
+    h_bases = None
+    if not args.no_e2e:
         h_bases = torch.empty(d_bases.numel(), dtype=torch.uint8, pin_memory=True)
         h_bases.copy_(d_bases)
         h_roff = torch.empty(args.reads + 1, dtype=torch.int64, pin_memory=True)
@@ -332,21 +541,45 @@ def main():
         hb, hr = h_bases.numpy(), h_roff.numpy().view(np.uint64)
         e_steps = args.steps
         for _ in range(2):
-            idx.query_reads_host(hb, hr, want_ids=False)  # warm-up (sizes the library's device workspace)
+            idx.query_reads_host(hb, hr, want_ids=False)  # warm-up (sizes the library's device workspace and staging)
         sync_all()
+        x0 = api.transfer_bytes()
         t0 = time.perf_counter()
         for _ in range(e_steps):
             _, ectr = idx.query_reads_host(hb, hr, want_ids=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        x1 = api.transfer_bytes()
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": world * total_kmers * e_steps / dt, "unit": "k-mers/s",
-               "h2d_bytes_per_step": int(h_bases.numel() + 8 * (args.reads + 1)), "d2h_bytes_per_step": 8 * api.N_CTR,
-               "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps, "mode": "bool (file_query counters), pinned host reads",
+               "h2d_bytes_per_step": (x1[0] - x0[0]) // e_steps, "d2h_bytes_per_step": (x1[1] - x0[1]) // e_steps,
+               "ascii_bytes_per_step": int(h_bases.numel()), "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps,
+               "mode": "bool (file_query counters), pinned host reads; part of the batch crosses PCIe 2-bit packed by the host cores (bytes as counted by the library)",
+               "host_threads_near_gpu": len(cpus) if cpus else None,
                "found": int(ectr[api.CTR_FOUND]), "not_found": int(ectr[api.CTR_NOT_FOUND])}
+
+    # ---- file_query(path): 2-line FASTA file on tmpfs through kmer_Set_Light::file_query's replacement (N = 1) ----
+    fq = None
+    if rank == 0 and world == 1 and not args.no_file_query:
+        try:
+            src = h_bases.numpy() if h_bases is not None else d_bases.cpu().numpy()
+            path = os.path.join(tmpdir, "reads.fa")
+            fasta_of(src.reshape(args.reads, args.read_len)).tofile(path)
+            fbytes = os.path.getsize(path)
+            idx.query_file_host(path)  # warm-up: page cache, pinned buffers
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                c = idx.query_file_host(path)
+            dt = (time.perf_counter() - t0) / reps
+            os.remove(path)
+            fq = {"value": total_kmers / dt, "unit": "k-mers/s", "seconds": dt, "file_bytes": fbytes, "file_GB_per_s": fbytes / dt / 1e9,
+                  "found": int(c[0]), "not_found": int(c[1]), "note": "blight_query_file_host: streaming reader -> record cut -> H2D / kernel overlap, wall clock"}
+        except Exception as ex:
+            fq = {"value": None, "error": repr(ex)}
 
     # ---- CPU baseline: the reference's query code on the host cores (rank 0, N=1 only) ----
     cpu = None
@@ -355,27 +588,33 @@ def main():
             import oracle
             n_s = min(args.cpu_sample_reads, args.reads)
             sb = d_bases[: n_s * args.read_len].cpu().numpy()
-            so = np.arange(n_s + 1, dtype=np.uint64) * np.uint64(args.read_len)
+            if not os.path.exists(blob):
+                flat.save(blob)
             if oracle.reference_available():
-                if not os.path.exists(blob):
-                    flat.save(blob)
-                ref = oracle.Reference.from_blob(blob, args.k, args.m)
-                threads = os.cpu_count() or ref.max_threads()
-                ref.query_reads(sb[: 2000 * args.read_len], so[:2001], threads=threads, want_ids=False)
-                _, f, nf, sec = ref.query_reads(sb, so, threads=threads, want_ids=False)
-                kind = "reference"
+                cpu, cpu_fq = reference_measure(blob, args.k, args.m, sb, n_s, args.read_len)
+                cpu["file_query"] = cpu_fq
             else:
                 port = oracle.CPort(blob)
-                threads = 1
                 n_s = min(n_s, 20000)
+                so = np.arange(n_s + 1, dtype=np.uint64) * np.uint64(args.read_len)
                 t0 = time.perf_counter()
-                _, c3 = port.query_reads(sb[: n_s * args.read_len], so[: n_s + 1], want_ids=False)
+                port.query_reads(sb[: n_s * args.read_len], so, want_ids=False)
                 sec = time.perf_counter() - t0
-                kind = "port"
-            cpu = {"value": n_s * kpr / sec, "unit": "k-mers/s", "cores": threads, "kind": kind,
-                   "sample": f"first {n_s} reads of the step ({n_s * kpr} k-mers), in-memory OpenMP loop over query_sequence_bool, {sec:.2f} s"}
+                cpu = {"value": n_s * kpr / sec, "unit": "k-mers/s", "cores": 1, "kind": "port",
+                       "sample": f"first {n_s} reads of the step ({n_s * kpr} k-mers), single-threaded C restatement, {sec:.2f} s"}
         except Exception as ex:  # the baseline is reported, never required
             cpu = {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+    dev_bytes, layout = idx.info["device_bytes"], idx.info["layout"]
+    # ---- partition mode (N > 1) ----
+    pm = None
+    if world > 1 and not args.no_partition:
+        del idx, d_bases, d_roff, d_koff, h_bases
+        torch.cuda.empty_cache()
+        try:
+            pm = partition_leg(args, rank, world, local, dev)
+        except Exception as ex:
+            pm = {"error": repr(ex)}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -383,11 +622,11 @@ def main():
         balg = b_alg(args.b, args.k) - (0.0 if headline_ids else 8.0 - 0.125)  # counters instead of an int64 id per k-mer
         kernel_ms = ms / args.steps  # the step is exactly one launch of the read kernel per GPU
         achieved = balg * total_kmers / (kernel_ms * 1e-3) / 1e9
-        kname = "k_reads_sk<ids>" if headline_ids else "k_reads_sk<count>"
-        if part is not None:
-            kname = "k_dispatch_runs + k_runs_lookup" + (" + k_scatter_runs" if headline_ids else "")
+        info_d = {"layout": layout}
+        kname = read_kernel_name(info_d, headline_ids, args.k, args.m)
         default_cfg = (args.genome, args.reads, args.read_len, args.k, args.m, args.n, args.b) == (100_000_000, 10_000_000, 150, 31, 7, 5, 6)
-        traffic = ncu_traffic(kname) if default_cfg and part is None else None
+        default_layout = layout == (api.LAYOUT_POS_ID | api.LAYOUT_FILTER | api.LAYOUT_EXACT_POS) and not os.environ.get("BLIGHT_FILTER_BITS")
+        traffic = ncu_traffic(kname) if default_cfg and default_layout else None
         line = {
             "metric": "queried k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -396,19 +635,23 @@ def main():
                          "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
                          "algorithmic_bytes_per_launch": balg * total_kmers, "peak_source": peak_src, "kernel": kname,
                          "bytes_per_kmer_algorithmic": balg, "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "file_query": fq, "gpu_launches": int(launches), "clocks": clocks,
             "ids_mode": None if (args.count_only or args.ids_only) else {
                 "value": world * total_kmers * args.steps / (ids_ms * 1e-3), "unit": "k-mers/s", "ms_per_step": ids_ms / args.steps,
-                "kernel": "k_reads_sk<ids>" if part is None else "k_dispatch_runs + k_runs_lookup + k_scatter_runs", "note": "query_sequence_hash semantics: one int64 id per k-mer written to HBM (9.6 GB per step)"},
-            "found_fraction": found_frac, "index": {"number_kmer": info["number_kmer"], "device_bytes": idx.info["device_bytes"],
-                                                     "build_seconds": build_s},
+                "kernel": read_kernel_name(info_d, True, args.k, args.m), "note": "query_sequence_hash semantics: one int64 id per k-mer written to HBM (9.6 GB per step)"},
+            "found_fraction": found_frac,
+            "index": {"number_kmer": info["number_kmer"], "device_bytes": dev_bytes, "bits_per_kmer": 8.0 * dev_bytes / max(1, info["number_kmer"]),
+                      "layout": {"pos_id": bool(layout & api.LAYOUT_POS_ID), "filter": bool(layout & api.LAYOUT_FILTER), "exact_pos": bool(layout & api.LAYOUT_EXACT_POS)},
+                      "reference_arrays_bits_per_kmer": (info["positions_bits"] + info["mphf_bits"] + 2 * info["total_nuc"]) / max(1, info["number_kmer"]),
+                      "build_seconds": build_s, "upload_seconds": upload_s},
+            "partition_mode": pm,
         }
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     import shutil
-    shutil.rmtree(tmpdir, ignore_errors=True)  # rank 0's holds the index blob (and the slices of --partition)
+    shutil.rmtree(tmpdir, ignore_errors=True)  # rank 0's holds the index blob
 
 
 if __name__ == "__main__":

@@ -24,10 +24,13 @@ SYMBOLS = [
     "blight_version", "blight_last_error", "blight_check_params", "blight_flat_build_file", "blight_flat_build_seqs", "blight_flat_build_spans",
     "blight_flat_save", "blight_flat_load", "blight_flat_free", "blight_flat_info", "blight_flat_compare",
     "blight_flat_slice", "blight_flat_group_sizes", "blight_index_upload", "blight_index_upload_opts", "blight_index_free", "blight_index_info",
-    "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads",
+    "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads", "blight_query_reads_packed",
+    "blight_query_sequence_bool_host", "blight_transfer_bytes",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
-    "blight_consume_reads", "blight_gather_reads", "blight_fasta_cut_stream", "blight_part_dispatch", "blight_part_lookup", "blight_part_scatter", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
+    "blight_consume_reads", "blight_gather_reads", "blight_fasta_cut_stream", "blight_part_dispatch", "blight_part_lookup", "blight_part_lookup_direct", "blight_part_scatter",
+    "blight_part_session_create", "blight_part_session_free", "blight_part_session_handles", "blight_part_session_connect_ipc",
+    "blight_part_session_connect_local", "blight_part_session_ids", "blight_part_session_query", "blight_part_session_status", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
 ]
 MAX_RANKS = 16
 RUN_RECORD_BYTES = 32
@@ -38,6 +41,16 @@ class PartRoute(C.Structure):
     _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("lb", C.c_uint32), ("reserved", C.c_uint32),
                 ("cuts", C.c_uint32 * (MAX_RANKS + 1)), ("inbox", C.c_void_p * MAX_RANKS), ("cap", C.c_uint64),
                 ("kcap", C.c_uint64), ("side", C.c_void_p)]
+
+
+class PartConfig(C.Structure):
+    """blight_part_config (include/blight_b200.h)"""
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("lb", C.c_uint32), ("reserved", C.c_uint32),
+                ("cuts", C.c_uint32 * (MAX_RANKS + 1)), ("sub_positions", C.c_uint64), ("cap", C.c_uint64),
+                ("ids_capacity", C.c_uint64)]
+
+
+PART_OVERFLOW, PART_TIMEOUT = 1, 2
 
 
 class BlightError(RuntimeError):
@@ -112,6 +125,10 @@ def lib() -> C.CDLL:
     L.blight_query_kmers_mini.argtypes = [vp, vp, vp, u64, vp, vp]
     L.blight_reads_to_kmers.argtypes = [u32, u32, vp, vp, vp, u64, u64, vp, vp, vp, vp]
     L.blight_query_reads.argtypes = [vp, vp, vp, vp, u64, u64, u64, vp, vp, vp]
+    L.blight_query_reads_packed.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp, vp]
+    L.blight_query_sequence_bool_host.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.blight_transfer_bytes.argtypes = [C.POINTER(u64), C.POINTER(u64)]
+    L.blight_transfer_bytes.restype = None
     L.blight_query_fasta_host.argtypes = [vp, vp, u64, vp]
     L.blight_query_file_host.argtypes = [vp, cp, vp]
     L.blight_query_sequence_host.argtypes = [vp, vp, u64, vp, C.POINTER(u64)]
@@ -127,6 +144,17 @@ def lib() -> C.CDLL:
     L.blight_part_dispatch.argtypes = [u32, u32, vp, vp, vp, u64, u64, u64, u64, C.POINTER(PartRoute), vp, vp, vp, vp]
     L.blight_part_lookup.argtypes = [vp, u32, C.POINTER(vp), vp, C.POINTER(vp), u64, u64, vp, vp]
     L.blight_part_scatter.argtypes = [vp, u64, vp, vp, u64, u32, u64, vp, vp, vp]
+    L.blight_part_lookup_direct.argtypes = [vp, u32, C.POINTER(vp), vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), u64, u64, vp, vp]
+    L.blight_part_session_create.argtypes = [vp, C.POINTER(PartConfig), C.POINTER(vp)]
+    L.blight_part_session_free.argtypes = [vp]
+    L.blight_part_session_free.restype = None
+    L.blight_part_session_handles.argtypes = [vp, C.c_char_p]
+    L.blight_part_session_connect_ipc.argtypes = [vp, u32, C.c_char_p, u64]
+    L.blight_part_session_connect_local.argtypes = [vp, u32, vp]
+    L.blight_part_session_ids.argtypes = [vp]
+    L.blight_part_session_ids.restype = vp
+    L.blight_part_session_query.argtypes = [vp, vp, vp, vp, u64, u64, u64, vp, vp]
+    L.blight_part_session_status.argtypes = [vp, C.POINTER(u32), C.c_int, vp]
     L.blight_peer_alloc.argtypes = [u64, C.POINTER(vp), C.c_char_p]
     L.blight_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.blight_peer_close.argtypes = [vp]
@@ -146,6 +174,13 @@ def _check(rc: int):
 
 def launch_count() -> int:
     return int(lib().blight_launch_count())
+
+
+def transfer_bytes():
+    """(host->device, device->host) bytes copied by the host-buffer entry points since load."""
+    a, b = C.c_uint64(), C.c_uint64()
+    lib().blight_transfer_bytes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
 
 
 class FlatIndex:
@@ -340,6 +375,26 @@ class DeviceIndex:
         _check(lib().blight_query_sequence_host(self._h, buf.ctypes.data, len(buf), out.ctypes.data, C.byref(n)))
         return out[:n.value]
 
+    def query_sequence_bool_host(self, seq):
+        """query_sequence_bool: (found, not_found) of one sequence, counted on the device."""
+        if isinstance(seq, str):
+            seq = seq.encode()
+        buf = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        f, nf = C.c_uint64(), C.c_uint64()
+        _check(lib().blight_query_sequence_bool_host(self._h, buf.ctypes.data, len(buf), C.byref(f), C.byref(nf)))
+        return int(f.value), int(nf.value)
+
+    def query_reads_packed(self, packed, read_off, total_bases: int, kmer_off=None, total_kmers=0, ids=None, ctr=None, want_ids=True, stream=None):
+        """Reads held as 2-bit codes on the device (int32 CUDA tensor, 16 bases per word, first base in the high bits)."""
+        import torch
+        if ctr is None:
+            ctr = torch.zeros(N_CTR, dtype=torch.int64, device=packed.device)
+        if want_ids and ids is None:
+            ids = torch.empty(max(int(total_kmers), 1), dtype=torch.int64, device=packed.device)
+        _check(lib().blight_query_reads_packed(self._h, _ptr(packed), _ptr(read_off), _ptr(kmer_off), read_off.numel() - 1, int(total_bases),
+                                               _ptr(ids) if want_ids else 0, _ptr(ctr), _stream_handle(stream)))
+        return (ids if want_ids else None), ctr
+
     def query_reads_host(self, bases: np.ndarray, read_off: np.ndarray, want_ids=True):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
@@ -397,6 +452,68 @@ class PeerBuffer:
         if self.ptr and _lib is not None:
             (_lib.blight_peer_free if self._owner else _lib.blight_peer_close)(C.c_void_p(self.ptr))
         self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _DeviceView:
+    """A device pointer torch can view without a copy (the owner of the memory must outlive the tensor)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PartSession:
+    """One rank of the bucket-partitioned path (blight_part_session, csrc/part_session.cu): peer-visible inbox / mailbox /
+    id array, the peers' buffers, and the per-batch pipeline ordered by device-side flags."""
+
+    def __init__(self, index: "DeviceIndex", world: int, rank: int, lb: int, cuts: Sequence[int], sub_positions: int, cap: int,
+                 ids_capacity: int = 0):
+        cfg = PartConfig()
+        cfg.world, cfg.rank, cfg.lb, cfg.sub_positions, cfg.cap, cfg.ids_capacity = world, rank, lb, sub_positions, cap, ids_capacity
+        for i, c in enumerate(cuts):
+            cfg.cuts[i] = c
+        h = C.c_void_p()
+        _check(lib().blight_part_session_create(index._h, C.byref(cfg), C.byref(h)))
+        self._h, self.index, self.world, self.rank = h, index, world, rank
+        self.sub_positions, self.cap, self.ids_capacity = sub_positions, cap, ids_capacity
+
+    def handles(self) -> bytes:
+        buf = C.create_string_buffer(192)
+        _check(lib().blight_part_session_handles(self._h, buf))
+        return buf.raw
+
+    def connect_ipc(self, peer: int, handles: bytes, peer_ids_capacity: int):
+        _check(lib().blight_part_session_connect_ipc(self._h, peer, handles, peer_ids_capacity))
+
+    def connect_local(self, peer: int, other: "PartSession"):
+        _check(lib().blight_part_session_connect_local(self._h, peer, other._h))
+
+    def ids_tensor(self, device):
+        """int64 torch view of this rank's id array (no copy)."""
+        import torch
+        p = lib().blight_part_session_ids(self._h)
+        if not p:
+            return None
+        return torch.as_tensor(_DeviceView(p, self.ids_capacity * 8), device=device).view(torch.int64)
+
+    def query(self, bases, read_off, kmer_off, n_sub: int, ctr, stream=None):
+        _check(lib().blight_part_session_query(self._h, _ptr(bases), _ptr(read_off), _ptr(kmer_off), read_off.numel() - 1, bases.numel(),
+                                               n_sub, _ptr(ctr), _stream_handle(stream)))
+
+    def status(self, reset: bool = True, stream=None) -> int:
+        f = C.c_uint32()
+        _check(lib().blight_part_session_status(self._h, C.byref(f), int(reset), _stream_handle(stream)))
+        return int(f.value)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.blight_part_session_free(self._h)
+            self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -481,8 +598,9 @@ class KmerSetLight:
         return ids
 
     def query_sequence_bool(self, query: str):
-        ids = self.query_sequence_hash(query)
-        return int((ids >= 0).sum()), int((ids < 0).sum())
+        f, nf = self.index.query_sequence_bool_host(query)
+        self.number_query += f + nf
+        return f, nf
 
     def query_kmer_hash(self, canon: int) -> int:
         self.number_query += 1

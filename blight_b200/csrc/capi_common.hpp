@@ -17,4 +17,10 @@ int flat_slice(const FlatIndex& f, uint64_t g_begin, uint64_t g_end, FlatIndex& 
 // stream_query.cu: file_query(path) chunk by chunk (reader thread -> parallel record cut -> H2D / kernel overlap)
 int stream_file_query(const struct ::blight_index* idx, const char* path, uint64_t* ctr);
 void stream_ctx_free(void* ctx);
+// host_query.cu: the contexts of the host-buffer entry points, created on first use and kept with the index
+void host_pool_free(void* pool);
+// a batch of records of a text in host memory ([beg[i], end[i]), beg has n+1 entries; end == null: end[i] = beg[i+1]) through
+// the read kernels: H2D (chunked, overlapped, optionally 2-bit packed on the host), kernels, D2H of the counters (and ids)
+int host_query_records(const struct ::blight_index* idx, const char* text, uint64_t len, const uint64_t* beg, const uint64_t* end,
+                       uint64_t n, const uint64_t* koff, int64_t* ids_out, uint64_t total_kmers, uint64_t* ctr, bool allow_pack);
 }  // namespace blight

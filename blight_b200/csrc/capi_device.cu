@@ -296,6 +296,7 @@ void blight_index_free(blight_index* idx) {
 	cudaFree(idx->d_fbk); cudaFree(idx->d_fbv); cudaFree(idx->d_valid); cudaFree(idx->d_pos_id); cudaFree(idx->d_filter);
 	for (void* w : idx->ws) cudaFree(w);
 	if (idx->stream_ctx) stream_ctx_free(idx->stream_ctx);
+	if (idx->host_pool) host_pool_free(idx->host_pool);
 	if (idx->host_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->host_stream));
 	if (idx->copy_stream) cudaStreamDestroy(static_cast<cudaStream_t>(idx->copy_stream));
 	if (idx->ev_copy) cudaEventDestroy(static_cast<cudaEvent_t>(idx->ev_copy));
@@ -335,8 +336,9 @@ int blight_reads_to_kmers(uint32_t k, uint32_t m, const char* d_bases, const uin
 	std::string err;
 	int rc = check_params(p, &err);
 	if (rc != BL_OK) return fail(rc, err);
-	rc = launch_reads(nullptr, k, m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, d_canon, d_mini, nullptr, d_ctr,
-	                  static_cast<cudaStream_t>(stream));
+	ReadBatch B;
+	B.d_bases = d_bases; B.d_read_off = d_read_off; B.d_kmer_off = d_kmer_off; B.n_reads = n_reads; B.total_bases = total_bases;
+	rc = launch_reads(nullptr, k, m, B, d_canon, d_mini, nullptr, d_ctr, static_cast<cudaStream_t>(stream));
 	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
 }
 
@@ -346,8 +348,19 @@ int blight_query_reads(const blight_index* idx, const char* d_bases, const uint6
 	(void)total_kmers;
 	if (!idx || (n_reads && (!d_bases || !d_read_off || !d_ctr || (d_ids && !d_kmer_off)))) return fail(BL_ERR_INVALID_ARG, "null argument");
 	DeviceGuard guard(idx->device);
-	int rc = launch_reads(&idx->v, idx->v.k, idx->v.m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, nullptr, nullptr,
-	                      d_ids, d_ctr, static_cast<cudaStream_t>(stream));
+	ReadBatch B;
+	B.d_bases = d_bases; B.d_read_off = d_read_off; B.d_kmer_off = d_kmer_off; B.n_reads = n_reads; B.total_bases = total_bases;
+	int rc = launch_reads(&idx->v, idx->v.k, idx->v.m, B, nullptr, nullptr, d_ids, d_ctr, static_cast<cudaStream_t>(stream));
+	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
+}
+
+int blight_query_reads_packed(const blight_index* idx, const uint32_t* d_packed, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
+                              uint64_t n_reads, uint64_t total_bases, int64_t* d_ids, uint64_t* d_ctr, void* stream) {
+	if (!idx || (n_reads && (!d_packed || !d_read_off || !d_ctr || (d_ids && !d_kmer_off)))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	DeviceGuard guard(idx->device);
+	ReadBatch B;
+	B.d_packed = d_packed; B.d_read_off = d_read_off; B.d_kmer_off = d_kmer_off; B.n_reads = n_reads; B.total_bases = total_bases;
+	int rc = launch_reads(&idx->v, idx->v.k, idx->v.m, B, nullptr, nullptr, d_ids, d_ctr, static_cast<cudaStream_t>(stream));
 	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
 }
 
@@ -358,8 +371,9 @@ int blight_consume_reads(const blight_index* idx, const char* d_bases, const uin
 	if (kind == BLIGHT_CONSUME_COLOR && (n_colors == 0 || color >= n_colors)) return fail(BL_ERR_INVALID_ARG, "color out of range");
 	if (!idx->v.pos_id || idx->v.k - idx->v.m + 1 < 8) return fail(BL_ERR_INVALID_ARG, "the fused consumers need the position->id table (N < 2^32-1, BLIGHT_POS_ID) and k-m+1 >= 8");
 	DeviceGuard guard(idx->device);
-	int rc = launch_reads_sink(idx->v, kind, d_bases, d_read_off, nullptr, n_reads, total_bases, d_table, n_colors, color, nullptr, d_ctr,
-	                           static_cast<cudaStream_t>(stream));
+	ReadBatch B;
+	B.d_bases = d_bases; B.d_read_off = d_read_off; B.n_reads = n_reads; B.total_bases = total_bases;
+	int rc = launch_reads_sink(idx->v, kind, B, d_table, n_colors, color, nullptr, d_ctr, static_cast<cudaStream_t>(stream));
 	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
 }
 
@@ -368,187 +382,10 @@ int blight_gather_reads(const blight_index* idx, const char* d_bases, const uint
 	if (!idx || !d_table || !d_out || !d_ctr || (n_reads && (!d_bases || !d_read_off || !d_kmer_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (!idx->v.pos_id || idx->v.k - idx->v.m + 1 < 8) return fail(BL_ERR_INVALID_ARG, "the fused consumers need the position->id table (N < 2^32-1, BLIGHT_POS_ID) and k-m+1 >= 8");
 	DeviceGuard guard(idx->device);
-	int rc = launch_reads_sink(idx->v, 2, d_bases, d_read_off, d_kmer_off, n_reads, total_bases, const_cast<uint32_t*>(d_table), 0, 0, d_out, d_ctr,
-	                           static_cast<cudaStream_t>(stream));
+	ReadBatch B;
+	B.d_bases = d_bases; B.d_read_off = d_read_off; B.d_kmer_off = d_kmer_off; B.n_reads = n_reads; B.total_bases = total_bases;
+	int rc = launch_reads_sink(idx->v, 2, B, const_cast<uint32_t*>(d_table), 0, 0, d_out, d_ctr, static_cast<cudaStream_t>(stream));
 	return rc == BL_OK ? rc : fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
-}
-
-// ---- host-buffer entry points -----------------------------------------------------------------------------
-
-namespace {
-
-// Grow-only device scratch of the host-buffer entry points (guarded by the index's host mutex).
-int ws_reserve(const blight_index* idx, int slot, size_t bytes, void** out) {
-	blight_index* m = const_cast<blight_index*>(idx);
-	if (m->ws_cap[slot] < bytes) {
-		if (m->ws[slot]) cudaFree(m->ws[slot]);
-		m->ws[slot] = nullptr; m->ws_cap[slot] = 0;
-		const size_t cap = bytes + bytes / 8 + 4096;
-		cudaError_t e = cudaMalloc(&m->ws[slot], cap);
-		if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
-		m->ws_cap[slot] = cap;
-	}
-	*out = m->ws[slot];
-	return BL_OK;
-}
-
-// Runs the reads kernel on a host buffer whose reads are [beg[i], end[i]) (beg has n+1 entries; end == null means
-// end[i] = beg[i+1]). H2D of the buffer and the offsets, one kernel, D2H of counters (and ids) — all on the
-// index's internal stream, inside this call.
-int run_host_reads(const blight_index* idx, const char* text, uint64_t len, const uint64_t* beg, const uint64_t* end,
-                   uint64_t n, const uint64_t* koff, int64_t* ids_out, uint64_t total_kmers, uint64_t* ctr) {
-	std::memset(ctr, 0, sizeof(uint64_t) * BLIGHT_N_CTR);
-	if (n == 0 || len == 0) return BL_OK;
-	DeviceGuard guard(idx->device);
-	std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(idx->host_mutex));
-	cudaStream_t st = static_cast<cudaStream_t>(idx->host_stream);
-	void *d_text = nullptr, *d_beg = nullptr, *d_end = nullptr, *d_koff = nullptr, *d_ctr = nullptr, *d_ids = nullptr;
-	int rc;
-	if ((rc = ws_reserve(idx, 0, len + 64, &d_text)) != BL_OK) return rc;
-	if ((rc = ws_reserve(idx, 1, (n + 1) * 8, &d_beg)) != BL_OK) return rc;
-	if (end && (rc = ws_reserve(idx, 2, n * 8, &d_end)) != BL_OK) return rc;
-	if ((rc = ws_reserve(idx, 3, BLIGHT_N_CTR * 8, &d_ctr)) != BL_OK) return rc;
-	if (ids_out) {
-		if ((rc = ws_reserve(idx, 4, (n + 1) * 8, &d_koff)) != BL_OK) return rc;
-		if ((rc = ws_reserve(idx, 5, std::max<uint64_t>(total_kmers, 1) * 8, &d_ids)) != BL_OK) return rc;
-	}
-	// The read offsets travel with the text, chunk by chunk (80 MB for 10 M reads would otherwise hold the first kernel back
-	// by 1.5 ms). Entries that have not arrived yet read as +infinity, which is what the kernel's search wants them to be:
-	// every read they describe starts past the positions it is looking for.
-	CU(cudaMemsetAsync(d_beg, 0xFF, (n + 1) * 8, st));
-	CU(cudaMemsetAsync(d_ctr, 0, BLIGHT_N_CTR * 8, st));
-	uint64_t off_done = 0;  // entries of beg / end / koff already copied
-	// The text goes over in chunks on a second stream; the kernel for chunk c (k-mers starting inside it) waits only
-	// for that chunk (+ a halo), so the copy of chunk c+1 overlaps the lookups of chunk c.
-	cudaStream_t cs = static_cast<cudaStream_t>(idx->copy_stream);
-	uint64_t chunk = 64ull << 20;  // a multiple of kReadsStrip
-	if (const char* e = getenv("BLIGHT_HOST_CHUNK_KB")) {  // tuning / test knob
-		const uint64_t kb = strtoull(e, nullptr, 10);
-		if (kb) chunk = ((kb << 10) + kReadsStrip - 1) / kReadsStrip * kReadsStrip;
-	}
-	const uint64_t halo = kReadsStrip;
-	CU(cudaEventRecord(static_cast<cudaEvent_t>(idx->ev_ws), st));  // the copy must not overtake the previous call's kernels
-	CU(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(idx->ev_ws), 0));
-	uint64_t copied = 0;
-	// the first chunks are small (4 MB, doubling up to `chunk`): the first kernel starts after 0.1 ms of copy instead of 1.2 ms
-	uint64_t step = std::min<uint64_t>(chunk, 4ull << 20);
-	for (uint64_t c0 = 0; c0 < len;) {
-		const uint64_t c1 = std::min(len, c0 + step);
-		const uint64_t upto = std::min(len, c1 + halo);
-		if (upto > copied) {
-			CU(cudaMemcpyAsync(static_cast<char*>(d_text) + copied, text + copied, upto - copied, cudaMemcpyHostToDevice, cs));
-			copied = upto;
-		}
-		{
-			// every read that starts before `upto`, and the entry after them
-			const uint64_t need = std::min<uint64_t>(n + 1, uint64_t(std::upper_bound(beg + off_done, beg + n + 1, upto) - beg) + 1);
-			if (need > off_done) {
-				CU(cudaMemcpyAsync(static_cast<uint64_t*>(d_beg) + off_done, beg + off_done, (need - off_done) * 8, cudaMemcpyHostToDevice, cs));
-				if (end && std::min(need, n) > off_done)
-					CU(cudaMemcpyAsync(static_cast<uint64_t*>(d_end) + off_done, end + off_done, (std::min(need, n) - off_done) * 8, cudaMemcpyHostToDevice, cs));
-				if (ids_out) CU(cudaMemcpyAsync(static_cast<uint64_t*>(d_koff) + off_done, koff + off_done, (need - off_done) * 8, cudaMemcpyHostToDevice, cs));
-				off_done = need;
-			}
-		}
-		CU(cudaEventRecord(static_cast<cudaEvent_t>(idx->ev_copy), cs));
-		CU(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(idx->ev_copy), 0));
-		rc = launch_reads(&idx->v, idx->v.k, idx->v.m, static_cast<const char*>(d_text), static_cast<const uint64_t*>(d_beg),
-		                  static_cast<const uint64_t*>(end ? d_end : nullptr), static_cast<const uint64_t*>(d_koff), n, len, nullptr,
-		                  nullptr, static_cast<int64_t*>(d_ids), static_cast<uint64_t*>(d_ctr), st, c0, c1);
-		if (rc != BL_OK) return fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error);
-		c0 = c1;
-		step = std::min<uint64_t>(chunk, step * 2);
-	}
-	if (ids_out && total_kmers) CU(cudaMemcpyAsync(ids_out, d_ids, total_kmers * 8, cudaMemcpyDeviceToHost, st));
-	CU(cudaMemcpyAsync(ctr, d_ctr, BLIGHT_N_CTR * 8, cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
-	if (ctr[BLIGHT_CTR_INVALID]) return fail(BL_ERR_INVALID_BASE, "Invalid char in DNA");
-	return BL_OK;
-}
-
-}  // namespace
-
-int blight_query_fasta_host(const blight_index* idx, const char* text, uint64_t len, uint64_t* ctr) {
-	if (!idx || !ctr || (len && !text)) return fail(BL_ERR_INVALID_ARG, "null argument");
-	std::vector<SeqView> recs;
-	split_fasta_records(text, len, recs);
-	std::vector<uint64_t> beg(recs.size() + 1), end(recs.size());
-	for (size_t i = 0; i < recs.size(); i++) { beg[i] = uint64_t(recs[i].p - text); end[i] = beg[i] + recs[i].len; }
-	beg[recs.size()] = len;
-	return run_host_reads(idx, text, len, beg.data(), end.data(), end.size(), nullptr, nullptr, 0, ctr);
-}
-
-int blight_query_file_host(const blight_index* idx, const char* path, uint64_t* ctr) {
-	if (!idx || !ctr || !path) return fail(BL_ERR_INVALID_ARG, "null argument");
-	{
-		const char* e = getenv("BLIGHT_FILE_QUERY");  // "whole": read the file into memory first (tests compare the two)
-		if (!e || e[0] != 'w') return stream_file_query(idx, path, ctr);
-	}
-	std::string storage, err;
-	std::vector<SeqView> recs;
-	int rc = read_fasta_records(path, storage, recs, &err);
-	if (rc != BL_OK) return fail(rc, err);
-	std::vector<uint64_t> beg(recs.size() + 1), end(recs.size());
-	for (size_t i = 0; i < recs.size(); i++) { beg[i] = uint64_t(recs[i].p - storage.data()); end[i] = beg[i] + recs[i].len; }
-	beg[recs.size()] = storage.size();
-	return run_host_reads(idx, storage.data(), storage.size(), beg.data(), end.data(), end.size(), nullptr, nullptr, 0, ctr);
-}
-
-int blight_query_reads_host(const blight_index* idx, const char* bases, const uint64_t* read_off, uint64_t n_reads,
-                            int64_t* ids_out, uint64_t* ctr) {
-	if (!idx || !ctr || (n_reads && (!bases || !read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
-	std::memset(ctr, 0, sizeof(uint64_t) * BLIGHT_N_CTR);
-	if (n_reads == 0) return BL_OK;
-	const uint32_t k = idx->v.k;
-	const uint64_t base0 = read_off[0];
-	std::vector<uint64_t> rebased, koff;
-	const uint64_t* beg = read_off;
-	if (base0 != 0) {
-		rebased.assign(read_off, read_off + n_reads + 1);
-		for (auto& v : rebased) v -= base0;
-		beg = rebased.data();
-	}
-	if (ids_out) {
-		koff.assign(n_reads + 1, 0);
-		for (uint64_t r = 0; r < n_reads; r++) {
-			const uint64_t l = read_off[r + 1] - read_off[r];
-			koff[r + 1] = koff[r] + (l >= k ? l - k + 1 : 0);
-		}
-	}
-	return run_host_reads(idx, bases + base0, read_off[n_reads] - base0, beg, nullptr, n_reads, ids_out ? koff.data() : nullptr, ids_out,
-	                      ids_out ? koff[n_reads] : 0, ctr);
-}
-
-int blight_query_sequence_host(const blight_index* idx, const char* seq, uint64_t len, int64_t* ids_out, uint64_t* n_out) {
-	if (!idx || !n_out || (len && !seq)) return fail(BL_ERR_INVALID_ARG, "null argument");
-	const uint32_t k = idx->v.k;
-	*n_out = len >= k ? len - k + 1 : 0;
-	if (*n_out == 0) return BL_OK;  // query.size() < k: empty result (blight.cpp:577-579)
-	if (!ids_out) return fail(BL_ERR_INVALID_ARG, "null argument");
-	uint64_t off[2] = {0, len}, ctr[BLIGHT_N_CTR];
-	return blight_query_reads_host(idx, seq, off, 1, ids_out, ctr);
-}
-
-int blight_query_kmers_host(const blight_index* idx, const uint64_t* canon, uint64_t n, int64_t* ids_out) {
-	if (!idx || (n && (!canon || !ids_out))) return fail(BL_ERR_INVALID_ARG, "null argument");
-	if (n == 0) return BL_OK;
-	DeviceGuard guard(idx->device);
-	std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(idx->host_mutex));
-	cudaStream_t st = static_cast<cudaStream_t>(idx->host_stream);
-	uint64_t* d_canon = nullptr; int64_t* d_ids = nullptr;
-	cudaError_t e;
-	auto cleanup = [&]() { cudaFree(d_canon); cudaFree(d_ids); };
-#define CUH(call) do { e = (call); if (e != cudaSuccess) { cleanup(); return cuda_fail(e, #call); } } while (0)
-	CUH(cudaMalloc(&d_canon, n * 8));
-	CUH(cudaMalloc(&d_ids, n * 8));
-	CUH(cudaMemcpyAsync(d_canon, canon, n * 8, cudaMemcpyHostToDevice, st));
-	int rc = launch_lookup_kmers(idx->v, d_canon, nullptr, n, d_ids, st);
-	if (rc != BL_OK) { cleanup(); return fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error); }
-	CUH(cudaMemcpyAsync(ids_out, d_ids, n * 8, cudaMemcpyDeviceToHost, st));
-	CUH(cudaStreamSynchronize(st));
-#undef CUH
-	cleanup();
-	return BL_OK;
 }
 
 uint64_t blight_launch_count(void) { return g_launches.load(); }

@@ -104,6 +104,7 @@ struct blight_index {
 	void* ev_ws = nullptr;
 	void* host_mutex = nullptr;
 	void* stream_ctx = nullptr;   // pinned / device buffers of the streaming file_query (stream_query.cu), created on first use
+	void* host_pool = nullptr;    // contexts (streams, staging, workspaces) of the host-buffer entry points (host_query.cu)
 	void* ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // grow-only scratch of the *_host entry points
 	size_t ws_cap[6] = {0, 0, 0, 0, 0, 0};
 };

@@ -23,10 +23,11 @@ constexpr int kStripKeys = kStrip + kMaxW;
 static_assert(kStripWords <= 32, "one lane packs one word");
 
 // first read r in [0, n_reads) with off[r+1] > p, i.e. the read containing base position p (or the gap before it).
-// Starts from the position a uniform read length would give and brackets the answer exponentially: 2-3 loads for
-// the usual near-uniform batches, a plain binary search in the worst case.
-__device__ __noinline__ uint64_t find_read(const uint64_t* __restrict__ off, uint64_t n_reads, double reads_per_base, uint64_t p) {
-	uint64_t g = (uint64_t)((double)p * reads_per_base);
+// Starts from the position a uniform read length would give (p0 = where read 0 of this array starts: the array may be a
+// window of a larger batch) and brackets the answer exponentially: 2-3 loads for the usual near-uniform batches, a plain
+// binary search in the worst case.
+__device__ __noinline__ uint64_t find_read(const uint64_t* __restrict__ off, uint64_t n_reads, double reads_per_base, uint64_t p, uint64_t p0) {
+	uint64_t g = (uint64_t)((double)(p > p0 ? p - p0 : 0) * reads_per_base);
 	if (g > n_reads - 1) g = n_reads - 1;
 	uint64_t lo, hi;  // invariant: answer in [lo, hi]
 	if (__ldg(off + g + 1) > p) {
@@ -171,7 +172,8 @@ template <bool WANT_O>
 __device__ __forceinline__ uint32_t strip_front(const StripSmem& S, uint32_t lane, uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                 const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                 const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
-                                                double reads_per_base, bool aligned16, uint64_t t0, uint32_t& invalid) {
+                                                double reads_per_base, uint64_t guess_p0, bool aligned16, const uint32_t* __restrict__ packed,
+                                                uint64_t t0, uint32_t& invalid) {
 	uint32_t* pack = S.pack;
 	uint32_t* bad = S.bad;
 	uint32_t* keys = S.keys;
@@ -181,8 +183,11 @@ __device__ __forceinline__ uint32_t strip_front(const StripSmem& S, uint32_t lan
 	const uint32_t n_pos = (uint32_t)min((uint64_t)kStrip, total_bases - t0);
 	const uint32_t n_load = (uint32_t)min((uint64_t)(kStrip + 32), total_bases - t0);
 	__syncwarp();
-	// A. pack
-	if (lane < kStripWords) {
+	// A. pack (or, when the caller already holds 2-bit codes — the host packer of the *_host entry points — copy)
+	if (lane < kStripWords && packed) {
+		pack[lane] = lane * 16 < n_load ? __ldcs(packed + (t0 >> 4) + lane) : 0u;
+		bad[lane] = 0;
+	} else if (lane < kStripWords) {
 		const uint32_t b0 = lane * 16;
 		uint32_t word = 0, badw = 0;
 		if (b0 < n_load) {
@@ -202,7 +207,7 @@ __device__ __forceinline__ uint32_t strip_front(const StripSmem& S, uint32_t lan
 	}
 	ReadCursor rc_;
 	rc_.r = 0;
-	if (lane == 0) rc_.r = find_read(read_off, n_reads, reads_per_base, t0);
+	if (lane == 0) rc_.r = find_read(read_off, n_reads, reads_per_base, t0, guess_p0);
 	rc_.r = __shfl_sync(0xffffffffu, rc_.r, 0);
 	__syncwarp();
 	// B. m-mer keys

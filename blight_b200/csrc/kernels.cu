@@ -192,7 +192,8 @@ template <int MODE, bool SMALL>
 __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                     const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                     const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
-                                                    uint64_t strip_lo, uint64_t strip_hi, bool aligned16, uint64_t* __restrict__ out_canon,
+                                                    uint64_t strip_lo, uint64_t strip_hi, bool aligned16, const uint32_t* __restrict__ packed,
+                                                    double reads_per_base, uint64_t guess_p0, uint64_t* __restrict__ out_canon,
                                                     uint32_t* __restrict__ out_mini, int64_t* __restrict__ out_ids,
                                                     uint64_t* __restrict__ ctr) {
 	__shared__ uint32_t s_pack[kWarps][kStripWords];  // 2-bit codes, 16 per word, first base in the high bits
@@ -206,7 +207,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 	const uint32_t w = k - m + 1;
 	const uint32_t mmask = (1u << (2 * m)) - 1u;
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
-	const double reads_per_base = (double)n_reads / (double)total_bases;
 	uint32_t found = 0, notfound = 0, invalid = 0;
 
 	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
@@ -214,8 +214,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 		const uint32_t n_pos = (uint32_t)min((uint64_t)kStrip, total_bases - t0);                        // positions owned by this strip
 		const uint32_t n_load = (uint32_t)min((uint64_t)(kStrip + 32), total_bases - t0);  // owned + halo (k-1 <= 30)
 		__syncwarp();
-		// A. pack: lane i converts bases [16i, 16i+16) of the strip
-		if (lane < kStripWords) {
+		// A. pack: lane i converts bases [16i, 16i+16) of the strip (or copies them when the caller holds 2-bit codes)
+		if (lane < kStripWords && packed) {
+			pack[lane] = lane * 16 < n_load ? __ldcs(packed + (t0 >> 4) + lane) : 0u;
+			bad[lane] = 0;
+		} else if (lane < kStripWords) {
 			const uint32_t b0 = lane * 16;
 			uint32_t word = 0, badw = 0;
 			if (b0 < n_load) {
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 		}
 		// read containing the first position of the strip (lane 0 searches, everybody starts from there)
 		uint64_t r = 0;
-		if (lane == 0) r = find_read(read_off, n_reads, reads_per_base, t0);
+		if (lane == 0) r = find_read(read_off, n_reads, reads_per_base, t0, guess_p0);
 		r = __shfl_sync(0xffffffffu, r, 0);
 		__syncwarp();
 		// B. m-mer keys
@@ -317,8 +320,8 @@ template <int MODE, bool SMALL>
 __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevIndexView I, uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                        const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                        const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
-                                                       uint64_t strip_lo, uint64_t strip_hi, bool aligned16,
-                                                       Sink K, uint64_t* __restrict__ ctr) {
+                                                       uint64_t strip_lo, uint64_t strip_hi, bool aligned16, const uint32_t* __restrict__ packed,
+                                                       double reads_per_base, uint64_t guess_p0, Sink K, uint64_t* __restrict__ ctr) {
 	constexpr bool kSlot = mode_wants_slot<MODE>(), kId = mode_wants_id<MODE>();
 	__shared__ uint32_t s_pack[kWarps][kStripWords];
 	__shared__ uint32_t s_bad[kWarps][kStripWords];
@@ -341,7 +344,6 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
 	const StripSmem S{pack, s_bad[wid], keys, s_run_q[wid], s_run_o[ow], s_runid8[wid]};
 	const uint32_t w = k - m + 1;
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
-	const double reads_per_base = (double)n_reads / (double)total_bases;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const bool filter_anchors = I.filter && (I.flags & kFlagFilterAnchors);
 	uint32_t found = 0, notfound = 0, invalid = 0;
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
 		const uint64_t t0 = strip * kStrip;
 		__syncwarp();
 		const uint32_t n_runs = strip_front<kSlot>(S, lane, k, m, bases, read_off, read_end, kmer_off, n_reads, total_bases,
-		                                                        reads_per_base, aligned16, t0, invalid);
+		                                                        reads_per_base, guess_p0, aligned16, packed, t0, invalid);
 		uint32_t n_res = 0;
 		if (n_runs > (uint32_t)kMaxRuns) {
 			// more runs than the table holds (many tiny reads): those k-mers take the plain lookup in C4
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
 						if (id != kTagOverflow) {
 							o = s_run_o[ow][id] + (q - s_run_q[wid][id]);
 						} else {
-							const uint64_t r = find_read(read_off, n_reads, reads_per_base, t0 + q);
+							const uint64_t r = find_read(read_off, n_reads, reads_per_base, t0 + q, guess_p0);
 							o = __ldg(kmer_off + r) + (t0 + q - __ldg(read_off + r));
 						}
 					}
@@ -543,18 +545,18 @@ int blocks_per_sm(K kernel) {
 	return nb;
 }
 
+double rpb_of(const ReadBatch& B) { return B.rpb > 0 ? B.rpb : (double)B.n_reads / (double)(B.total_bases ? B.total_bases : 1); }
+
 template <int MODE, bool SMALL>
-void launch_reads_plain(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
-                        const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
-                        uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
-                        cudaStream_t stream) {
+void launch_reads_plain(const DevIndexView& v, uint32_t k, uint32_t m, const ReadBatch& B, uint64_t strip_lo, uint64_t strip_hi, bool al,
+                        uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream) {
 	static const int per_sm = blocks_per_sm(k_reads<MODE, SMALL>);
 	const uint64_t n_strips = strip_hi - strip_lo;
 	const uint64_t want = (n_strips + kWarps - 1) / kWarps;
 	const uint64_t cap = (uint64_t)sm_count() * per_sm;  // persistent: one resident wave, warps stride over the strips
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
-	k_reads<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
-	                                                   strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr);
+	k_reads<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, B.d_bases, B.d_read_off, B.d_read_end, B.d_kmer_off, B.n_reads, B.total_bases,
+	                                                   strip_lo, strip_hi, al, B.d_packed, rpb_of(B), B.guess_p0, d_canon, d_mini, d_ids, d_ctr);
 }
 
 // Which read kernel serves a mode. Measured on B200 (100 M-k-mer index, b=6): counting mode 1.88e10 k-mers/s with the
@@ -571,29 +573,25 @@ bool use_superkmer_kernel(bool want_ids, bool has_pos_id) {
 }
 
 template <int MODE, bool SMALL>
-void launch_reads_sk(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
-                     const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
-                     uint64_t strip_lo, uint64_t strip_hi, bool al, const Sink& sink, uint64_t* d_ctr, cudaStream_t stream) {
+void launch_reads_sk(const DevIndexView& v, uint32_t k, uint32_t m, const ReadBatch& B, uint64_t strip_lo, uint64_t strip_hi, bool al,
+                     const Sink& sink, uint64_t* d_ctr, cudaStream_t stream) {
 	static const int per_sm = blocks_per_sm(k_reads_sk<MODE, SMALL>);
 	const uint64_t n_strips = strip_hi - strip_lo;
 	const uint64_t want = (n_strips + kWarps - 1) / kWarps;
 	const uint64_t cap = (uint64_t)sm_count() * per_sm;
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
-	k_reads_sk<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
-	                                                      strip_lo, strip_hi, al, sink, d_ctr);
+	k_reads_sk<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, B.d_bases, B.d_read_off, B.d_read_end, B.d_kmer_off, B.n_reads, B.total_bases,
+	                                                      strip_lo, strip_hi, al, B.d_packed, rpb_of(B), B.guess_p0, sink, d_ctr);
 }
 
 template <int MODE, bool SMALL>
-void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
-                    const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
-                    uint64_t strip_lo, uint64_t strip_hi, bool al, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr,
-                    cudaStream_t stream) {
+void launch_reads_t(const DevIndexView& v, uint32_t k, uint32_t m, const ReadBatch& B, uint64_t strip_lo, uint64_t strip_hi, bool al,
+                    uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream) {
 	if (MODE != kEmitPairs && v.valid && k - m + 1 >= 8 && use_superkmer_kernel(MODE == kLookupIds, v.pos_id != nullptr)) {
-		launch_reads_sk<MODE == kEmitPairs ? kLookupCount : MODE, SMALL>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases,
-		                                                                strip_lo, strip_hi, al, Sink{d_ids, nullptr, nullptr, 0, 0}, d_ctr, stream);
+		launch_reads_sk<MODE == kEmitPairs ? kLookupCount : MODE, SMALL>(v, k, m, B, strip_lo, strip_hi, al, Sink{d_ids, nullptr, nullptr, 0, 0}, d_ctr, stream);
 		return;
 	}
-	launch_reads_plain<MODE, SMALL>(v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
+	launch_reads_plain<MODE, SMALL>(v, k, m, B, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream);
 }
 
 }  // namespace
@@ -629,17 +627,16 @@ int launch_exact_positions(const DevIndexView& I, uint64_t n_buckets, uint64_t n
 	return check(e);
 }
 
-int launch_reads_sink(const DevIndexView& I, int kind, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
-                      uint64_t n_reads, uint64_t total_bases, uint32_t* d_table, uint32_t n_colors, uint32_t color, uint32_t* d_out32,
+int launch_reads_sink(const DevIndexView& I, int kind, const ReadBatch& B, uint32_t* d_table, uint32_t n_colors, uint32_t color, uint32_t* d_out32,
                       uint64_t* d_ctr, cudaStream_t stream) {
-	if (n_reads == 0 || total_bases == 0) return 0;
-	const uint64_t strip_hi = (total_bases + kStrip - 1) / kStrip;
-	const bool al = (reinterpret_cast<uintptr_t>(d_bases) & 15) == 0;
+	if (B.n_reads == 0 || B.total_bases == 0) return 0;
+	const uint64_t strip_hi = (B.total_bases + kStrip - 1) / kStrip;
+	const bool al = (reinterpret_cast<uintptr_t>(B.d_bases) & 15) == 0;
 	const Sink sink{nullptr, d_table, d_out32, n_colors, color};
-#define BL_SINK(MODE)                                                                                                              \
-	do {                                                                                                                            \
-		if (I.small) launch_reads_sk<MODE, true>(I, I.k, I.m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, 0, strip_hi, al, sink, d_ctr, stream); \
-		else launch_reads_sk<MODE, false>(I, I.k, I.m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases, 0, strip_hi, al, sink, d_ctr, stream);        \
+#define BL_SINK(MODE)                                                                                  \
+	do {                                                                                                \
+		if (I.small) launch_reads_sk<MODE, true>(I, I.k, I.m, B, 0, strip_hi, al, sink, d_ctr, stream); \
+		else launch_reads_sk<MODE, false>(I, I.k, I.m, B, 0, strip_hi, al, sink, d_ctr, stream);        \
 	} while (0)
 	if (kind == 0) BL_SINK(kConsumeCount);
 	else if (kind == 1) BL_SINK(kConsumeColor);
@@ -670,19 +667,18 @@ int launch_lookup_kmers(const DevIndexView& I, const uint64_t* d_canon, const ui
 	return check(e);
 }
 
-int launch_reads(const DevIndexView* I, uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off,
-                 const uint64_t* d_read_end, const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases,
-                 uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids, uint64_t* d_ctr, cudaStream_t stream, uint64_t pos_begin,
-                 uint64_t pos_end) {
-	if (n_reads == 0 || total_bases == 0) return 0;
-	if (pos_end > total_bases) pos_end = total_bases;
+int launch_reads(const DevIndexView* I, uint32_t k, uint32_t m, const ReadBatch& B, uint64_t* d_canon, uint32_t* d_mini, int64_t* d_ids,
+                 uint64_t* d_ctr, cudaStream_t stream, uint64_t pos_begin, uint64_t pos_end) {
+	if (B.n_reads == 0 || B.total_bases == 0) return 0;
+	if (pos_end > B.total_bases) pos_end = B.total_bases;
 	if (pos_begin >= pos_end) return 0;
-	if ((pos_begin % kStrip) != 0 || (pos_end < total_bases && (pos_end % kStrip) != 0)) return BLIGHT_ERR_INVALID_ARG;
+	if ((pos_begin % kStrip) != 0 || (pos_end < B.total_bases && (pos_end % kStrip) != 0)) return BLIGHT_ERR_INVALID_ARG;
+	if ((B.d_bases == nullptr) == (B.d_packed == nullptr)) return BLIGHT_ERR_INVALID_ARG;  // exactly one representation
 	const uint64_t strip_lo = pos_begin / kStrip, strip_hi = (pos_end + kStrip - 1) / kStrip;
 	DevIndexView v{};
 	if (I) v = *I;
-	const bool al = (reinterpret_cast<uintptr_t>(d_bases) & 15) == 0;
-#define BL_ARGS v, k, m, d_bases, d_read_off, d_read_end, d_kmer_off, n_reads, total_bases, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream
+	const bool al = (reinterpret_cast<uintptr_t>(B.d_bases) & 15) == 0;
+#define BL_ARGS v, k, m, B, strip_lo, strip_hi, al, d_canon, d_mini, d_ids, d_ctr, stream
 	if (!I) launch_reads_t<kEmitPairs, true>(BL_ARGS);
 	else if (d_ids) { if (v.small) launch_reads_t<kLookupIds, true>(BL_ARGS); else launch_reads_t<kLookupIds, false>(BL_ARGS); }
 	else { if (v.small) launch_reads_t<kLookupCount, true>(BL_ARGS); else launch_reads_t<kLookupCount, false>(BL_ARGS); }

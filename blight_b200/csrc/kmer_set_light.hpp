@@ -67,9 +67,10 @@ public:
 	}
 
 	std::pair<uint32_t, uint32_t> query_sequence_bool(const std::string& query) {
-		uint32_t good = 0, fail = 0;
-		for (int64_t id : query_sequence_hash(query)) (id >= 0 ? good : fail)++;
-		return {good, fail};
+		uint64_t good = 0, bad = 0;
+		raise(blight_query_sequence_bool_host(need(), query.data(), query.size(), &good, &bad));
+		number_query += good + bad;
+		return {(uint32_t)good, (uint32_t)bad};
 	}
 
 	int64_t query_kmer_hash(kmer_t canon) {

@@ -45,10 +45,11 @@ constexpr uint32_t kIdAbsent = 0xFFFFFFFFu;
 
 struct alignas(32) RunRec {
 	uint32_t bases[4];  // n + k - 1 bases, 2 bits each, first base in the high bits of bases[0]
-	uint32_t ko;        // k-mer offset of the run's first k-mer in the (source, owner) stream of this sub-batch
+	uint32_t ko;        // stream return: k-mer offset of the run's first k-mer in the (source, owner) stream of this sub-batch
+	                    // direct return: low half of the slot of the run's first k-mer in the source's id array
 	uint32_t mn;        // minimizer (bucket) of every k-mer of the run
 	uint32_t n_src;     // bits 0-7: k-mers in the run, bits 8-15: source rank
-	uint32_t spare;
+	uint32_t o_hi;      // direct return: high half of the slot
 };
 static_assert(sizeof(RunRec) == 32, "one record = one sector");
 
@@ -58,7 +59,8 @@ struct Route {
 	RunRec* inbox[kMaxRanks];  // this source's region in every owner's inbox (peer pointers)
 	uint64_t cap;              // records per region
 	uint64_t kcap;             // k-mers per return region
-	uint4* side;               // local: {o_lo, o_hi, ko, n} of record `slot` bound for owner d at [d * cap + slot]; null = counting
+	uint4* side;               // local: {o_lo, o_hi, ko, n} of record `slot` bound for owner d at [d * cap + slot]; null = counting / direct
+	uint32_t direct;           // ids return straight into this source's id array (the record carries the slot), no side table
 };
 
 __device__ __forceinline__ uint32_t owner_of(const Route& R, uint32_t mini) {
@@ -73,7 +75,8 @@ template <bool WANT_O>
 __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint32_t m, const char* __restrict__ bases,
                                                              const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                              const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
-                                                             uint64_t strip_lo, uint64_t strip_hi, bool aligned16, Route R,
+                                                             uint64_t strip_lo, uint64_t strip_hi, bool aligned16, const uint32_t* __restrict__ packed,
+                                                             double reads_per_base, uint64_t guess_p0, Route R,
                                                              unsigned long long* __restrict__ counts, uint64_t* __restrict__ ctr,
                                                              uint32_t* __restrict__ err) {
 	__shared__ uint32_t s_pack[kWarps][kStripWords];
@@ -91,7 +94,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 	const uint32_t w = k - m + 1;
 	const uint32_t nmax = min(64u - k + 1u, kMaxRecKmers);  // k-mers one record carries (64 bases)
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
-	const double reads_per_base = (double)n_reads / (double)total_bases;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	uint32_t invalid = 0, queries = 0;
 
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 		s_run_n[wid][lane] = 0;
 		s_run_n[wid][lane + 32] = 0;
 		const uint32_t n_runs = strip_front<WANT_O>(S, lane, k, m, bases, read_off, read_end, kmer_off, n_reads, total_bases, reads_per_base,
-		                                            aligned16, t0, invalid);
+		                                            guess_p0, aligned16, packed, t0, invalid);
 		// length of every run: each lane adds up its own 8 positions
 		{
 			const uint64_t tags = s_runid8[wid][lane];
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 				if (runid[qq] == kTagOverflow) {
 					q = qq; n = 1;
 					if (WANT_O) {
-						const uint64_t r = find_read(read_off, n_reads, reads_per_base, t0 + q);
+						const uint64_t r = find_read(read_off, n_reads, reads_per_base, t0 + q, guess_p0);
 						o = __ldg(kmer_off + r) + (t0 + q - __ldg(read_off + r));
 					}
 				}
@@ -180,10 +182,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 						const uint4 b = strip_bases64(S.pack, q + off);
 						uint4* dstp = reinterpret_cast<uint4*>(R.inbox[dst] + slot);
 						dstp[0] = b;
-						dstp[1] = make_uint4((uint32_t)ko, mn, nn | (R.rank << 8), 0u);
-						if (WANT_O) {
-							const uint64_t oo = o + off;
-							R.side[(uint64_t)dst * R.cap + slot] = make_uint4((uint32_t)oo, (uint32_t)(oo >> 32), (uint32_t)ko, nn);
+						const uint64_t oo = o + off;
+						if (WANT_O && R.direct) {
+							dstp[1] = make_uint4((uint32_t)oo, mn, nn | (R.rank << 8), (uint32_t)(oo >> 32));
+						} else {
+							dstp[1] = make_uint4((uint32_t)ko, mn, nn | (R.rank << 8), 0u);
+							if (WANT_O) R.side[(uint64_t)dst * R.cap + slot] = make_uint4((uint32_t)oo, (uint32_t)(oo >> 32), (uint32_t)ko, nn);
 						}
 					} else {
 						atomicOr(err, 1u);
@@ -207,7 +211,10 @@ struct OwnerArgs {
 	uint32_t world, pad;
 	uint64_t cap, kcap;               // records per inbox region, ids per return region
 	const RunRec* region[kMaxRanks];  // records received from every source
-	uint32_t* ret[kMaxRanks];         // this owner's return region at every source (peer pointers), unused in counting mode
+	uint32_t* ret[kMaxRanks];         // stream return: this owner's return region at every source (peer pointers)
+	int64_t* out[kMaxRanks];          // direct return: every source's id array (peer pointers) ...
+	uint64_t out_cap[kMaxRanks];      // ... and its length
+	uint32_t direct;
 };
 
 // k-mer at offset d of a record's bases
@@ -242,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 	__shared__ uint64_t s_okv[kWarps][32];
 	__shared__ uint16_t s_res[kWarps][kResCap];                 // work list: flattened indices waiting for the whole lookup
 	__shared__ uint32_t s_ids[WANT_IDS ? kWarps : 1][kMaxIds];  // the warp's answers, in the order they travel back
+	__shared__ uint64_t s_o[WANT_IDS ? kWarps : 1][32];         // direct return: slot of every run's first k-mer at the source
 
 	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t iw = WANT_IDS ? wid : 0;
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 			uint32_t* W = s_w[wid][lane];
 			W[0] = b.x; W[1] = b.y; W[2] = b.z; W[3] = b.w; W[4] = 0;
 			ko = h.x;
+			if (WANT_IDS) s_o[iw][lane] = ((uint64_t)h.w << 32) | h.x;
 			s_mn[wid][lane] = h.y < mn_limit ? h.y : 0u;  // (a slot the source dropped holds an older record or zeros: stay in bounds)
 			n = min(h.z & 0xFFu, kMaxRecKmers);
 		}
@@ -424,7 +433,19 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 			}
 			__syncwarp();
 		} while (n_res > 0 || base < n_ids);
-		if (WANT_IDS) {
+		if (WANT_IDS && A.direct) {
+			// the warp's answers straight into the source's id array (NVLink): the ids of a run are consecutive int64 slots, so
+			// lanes holding one run store one contiguous segment
+			int64_t* dst = A.out[src];
+			const uint64_t lim = A.out_cap[src];
+			const long long id0 = (long long)I.id_base;
+			for (uint32_t t = lane; t < n_ids; t += 32) {
+				const uint32_t run = run_of(s_incl[wid], t);
+				const uint64_t o = s_o[iw][run] + (t - (run ? s_incl[wid][run - 1] : 0u));
+				const uint32_t v = s_ids[iw][t];
+				if (o < lim) __stcs(reinterpret_cast<long long*>(dst + o), v == kIdAbsent ? -1ll : id0 + (long long)v);
+			}
+		} else if (WANT_IDS) {
 			// the warp's answers back to the source: one contiguous stream of 32-bit ids over NVLink
 			uint32_t* dst = A.ret[src] + ko0;
 			if ((uint64_t)ko0 + n_ids <= A.kcap)
@@ -537,11 +558,21 @@ extern "C" {
 int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
                          uint64_t n_reads, uint64_t total_bases, uint64_t pos_begin, uint64_t pos_end, const blight_part_route* route,
                          uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream) {
-	if (!route || !d_counts || !d_ctr || !d_err || (n_reads && (!d_bases || !d_read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	ReadBatch B;
+	B.d_bases = d_bases; B.d_read_off = d_read_off; B.d_kmer_off = d_kmer_off; B.n_reads = n_reads; B.total_bases = total_bases;
+	return part_dispatch_batch(k, m, B, pos_begin, pos_end, route, d_counts, d_ctr, d_err, stream);
+}
+
+}  // extern "C"
+
+namespace blight {
+int part_dispatch_batch(uint32_t k, uint32_t m, const ReadBatch& B, uint64_t pos_begin, uint64_t pos_end, const blight_part_route* route,
+                        uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream) {
+	const uint64_t n_reads = B.n_reads, total_bases = B.total_bases;
+	if (!route || !d_counts || !d_ctr || !d_err || (n_reads && ((!B.d_bases && !B.d_packed) || !B.d_read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (route->world == 0 || route->world > (uint32_t)kMaxRanks || route->rank >= route->world) return fail(BL_ERR_INVALID_ARG, "bad world / rank");
 	if (k < 8 || k > 32 || m >= k || k - m + 1 < 8 || k - m + 1 > 32) return fail(BL_ERR_INVALID_ARG, "partition mode needs 8 <= k <= 32 and 8 <= k-m+1 <= 32");
 	if (route->cap == 0 || route->cap >= (1ull << 24) || route->kcap >= (1ull << 32)) return fail(BL_ERR_INVALID_ARG, "region capacities: cap < 2^24 records, kcap < 2^32 k-mers");
-	if (d_kmer_off && !route->side) return fail(BL_ERR_INVALID_ARG, "id mode needs the side table");
 	if (n_reads == 0 || total_bases == 0) return BL_OK;
 	if (pos_end > total_bases) pos_end = total_bases;
 	if (pos_begin >= pos_end) return BL_OK;
@@ -549,37 +580,48 @@ int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint
 	Route R{};
 	R.world = route->world; R.rank = route->rank; R.lb = route->lb; R.cap = route->cap; R.kcap = route->kcap;
 	R.side = static_cast<uint4*>(route->side);
+	R.direct = (B.d_kmer_off && !route->side) ? 1u : 0u;  // id mode without a side table: the records carry the output slots
 	for (uint32_t i = 0; i <= route->world; i++) R.cuts[i] = route->cuts[i];
 	for (uint32_t i = 0; i < route->world; i++) {
 		if (!route->inbox[i]) return fail(BL_ERR_INVALID_ARG, "null inbox pointer");
 		R.inbox[i] = static_cast<RunRec*>(route->inbox[i]);
 	}
 	const uint64_t strip_lo = pos_begin / kStrip, strip_hi = (pos_end + kStrip - 1) / kStrip;
-	const bool al = (reinterpret_cast<uintptr_t>(d_bases) & 15) == 0;
+	const bool al = (reinterpret_cast<uintptr_t>(B.d_bases) & 15) == 0;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	const uint64_t want = (strip_hi - strip_lo + kWarps - 1) / kWarps;
-	if (d_kmer_off) {
+	const double rpb = B.rpb > 0 ? B.rpb : (double)n_reads / (double)total_bases;
+	if (B.d_kmer_off) {
 		static const int nb = per_sm(k_dispatch_runs<true>);
 		const uint64_t cap = (uint64_t)sm_count_() * nb;
-		k_dispatch_runs<true><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(k, m, d_bases, d_read_off, nullptr, d_kmer_off, n_reads, total_bases,
-			strip_lo, strip_hi, al, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err);
+		k_dispatch_runs<true><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(k, m, B.d_bases, B.d_read_off, B.d_read_end, B.d_kmer_off, n_reads,
+			total_bases, strip_lo, strip_hi, al, B.d_packed, rpb, B.guess_p0, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err);
 	} else {
 		static const int nb = per_sm(k_dispatch_runs<false>);
 		const uint64_t cap = (uint64_t)sm_count_() * nb;
-		k_dispatch_runs<false><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(k, m, d_bases, d_read_off, nullptr, nullptr, n_reads, total_bases,
-			strip_lo, strip_hi, al, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err);
+		k_dispatch_runs<false><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(k, m, B.d_bases, B.d_read_off, B.d_read_end, nullptr, n_reads,
+			total_bases, strip_lo, strip_hi, al, B.d_packed, rpb, B.guess_p0, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err);
 	}
 	g_launches++;
 	return finish("k_dispatch_runs");
 }
+}  // namespace blight
+
+extern "C" {
 
 int blight_part_lookup(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts, void* const* ret,
                        uint64_t cap, uint64_t kcap, uint64_t* d_ctr, void* stream) {
+	return blight_part_lookup_direct(idx, world, regions, d_counts, ret, nullptr, nullptr, cap, kcap, d_ctr, stream);
+}
+
+int blight_part_lookup_direct(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts, void* const* ret,
+                              void* const* out_ids, const uint64_t* out_caps, uint64_t cap, uint64_t kcap, uint64_t* d_ctr, void* stream) {
+	if (out_ids && (ret || !out_caps)) return fail(BL_ERR_INVALID_ARG, "direct return: pass out_ids + out_caps and no return regions");
 	const uint64_t max_records = (uint64_t)world * cap;
 	if (!idx || !regions || !d_counts || !d_ctr) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (world == 0 || world > (uint32_t)kMaxRanks) return fail(BL_ERR_INVALID_ARG, "bad world");
 	if (!idx->v.valid) return fail(BL_ERR_INVALID_ARG, "index has no valid-window bitmap");
-	if (ret && !idx->v.pos_id) return fail(BL_ERR_INVALID_ARG, "id mode of the partitioned path needs the position->id table (BLIGHT_POS_ID)");
+	if ((ret || out_ids) && !idx->v.pos_id) return fail(BL_ERR_INVALID_ARG, "id mode of the partitioned path needs the position->id table (BLIGHT_POS_ID)");
 	if (idx->v.k < 8) return fail(BL_ERR_INVALID_ARG, "partition mode needs k >= 8");
 	DeviceGuardLite guard(idx->device);
 	OwnerArgs A{};
@@ -589,7 +631,10 @@ int blight_part_lookup(const blight_index* idx, uint32_t world, const void* cons
 	for (uint32_t i = 0; i < world; i++) {
 		A.region[i] = static_cast<const RunRec*>(regions[i]);
 		A.ret[i] = ret ? static_cast<uint32_t*>(ret[i]) : nullptr;
+		A.out[i] = out_ids ? static_cast<int64_t*>(out_ids[i]) : nullptr;
+		A.out_cap[i] = out_ids ? out_caps[i] : 0;
 	}
+	A.direct = out_ids ? 1u : 0u;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	const uint64_t want = std::max<uint64_t>(1, ((max_records + 31) / 32 + world + kWarps - 1) / kWarps);
 	const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(d_counts);
@@ -599,7 +644,7 @@ int blight_part_lookup(const blight_index* idx, uint32_t world, const void* cons
 		const uint64_t cap = (uint64_t)sm_count_() * nb;                                                 \
 		k_runs_lookup<IDS, SM><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(idx->v, A, cnt, d_ctr); \
 	} while (0)
-	if (ret) { if (idx->v.small) BL_LAUNCH(true, true); else BL_LAUNCH(true, false); }
+	if (ret || out_ids) { if (idx->v.small) BL_LAUNCH(true, true); else BL_LAUNCH(true, false); }
 	else { if (idx->v.small) BL_LAUNCH(false, true); else BL_LAUNCH(false, false); }
 #undef BL_LAUNCH
 	g_launches++;

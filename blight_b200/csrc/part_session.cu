@@ -1,0 +1,313 @@
+// part_session.cu — one rank of the bucket-partitioned query path (BASELINE configs[4]) as an object behind
+// the C ABI: its peer-visible buffers, the connection to the other ranks' buffers, and the per-batch pipeline.
+//
+// The kernels are those of part_kernels.cu (k_dispatch_runs at the GPU holding the reads, k_runs_lookup at the owner of the
+// minimizer bucket; records and identifiers cross NVLink as peer-memory stores issued by the kernels themselves). What this
+// file adds is the ordering BETWEEN GPUs, without any collective library call on the data path:
+//
+//   k_publish_counts   (source, after its dispatch kernel)  stores, into every owner's mailbox, how many records it left in
+//                      that owner's inbox, fences at system scope, then stores the sub-batch's sequence number
+//   k_wait_counts      (owner, before its lookup kernel)    spins until every source's sequence number has arrived and
+//                      copies the counts next to the lookup kernel's arguments
+//
+// Stream order on every rank, sub-batch i using inbox half i & 1:   D(i)  P(i)  W(i)  L(i)
+//   (BLIGHT_PART_ORDER=ahead:  D(i+1)  L(i)  P(i+1)  W(i+1), so that the wait never sees the dispatch skew)
+// A source rewrites half b in D(i+2), which follows its own W(i+1); W(i+1) needs every rank's P(i+1), which that rank
+// issued after its L(i): nobody is still reading the half. No deadlock: every wait depends only on kernels that precede
+// the matching publish in the publisher's own stream.
+// The ranks are processes (torchrun: buffers exchanged as CUDA IPC handles) or devices of one process
+// (blight_comm, comm.cu: peer access).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "capi_common.hpp"
+#include "device_index.hpp"
+#include "kernels.hpp"
+
+using namespace blight;
+
+namespace {
+
+constexpr int kMaxRanks = BLIGHT_MAX_RANKS;
+constexpr int kMailSlots = 3;  // two inbox halves + the end-of-batch fence
+
+// Written by the peers, read by the owner. One per rank, inside its mailbox allocation.
+struct Mailbox {
+	unsigned long long count[kMailSlots][kMaxRanks];  // packed (records << 40 | k-mers) source s left for this owner
+	unsigned long long seq[kMailSlots][kMaxRanks];    // sequence number of the sub-batch those counts belong to
+};
+
+struct MailPtrs { Mailbox* m[kMaxRanks]; };
+
+__global__ void k_publish_counts(MailPtrs peers, const unsigned long long* __restrict__ counts, uint32_t world, uint32_t rank, uint32_t slot,
+                                 unsigned long long seq) {
+	const uint32_t d = threadIdx.x;
+	if (d >= world) return;
+	Mailbox* mb = peers.m[d];
+	mb->count[slot][rank] = counts ? counts[d] : 0ull;
+	__threadfence_system();  // the records of the dispatch kernel (earlier in this stream) and the count, before the flag
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&mb->seq[slot][rank]), "l"(seq) : "memory");
+}
+
+__global__ void k_wait_counts(const Mailbox* mb, uint32_t world, uint32_t slot, unsigned long long seq, unsigned long long* __restrict__ rcv,
+                              uint32_t* __restrict__ err, long long spin_limit) {
+	const uint32_t s = threadIdx.x;
+	if (s >= world) return;
+	const long long t0 = clock64();
+	unsigned long long got;
+	for (;;) {
+		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&mb->seq[slot][s]) : "memory");
+		if (got >= seq) break;
+		if (clock64() - t0 > spin_limit) { atomicOr(err, 2u); if (rcv) rcv[s] = 0; return; }  // a peer never arrived: give up loudly
+		__nanosleep(200);
+	}
+	if (rcv) rcv[s] = mb->count[slot][s];
+}
+
+int cu_fail(cudaError_t e, const char* what) { return fail(BL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cu_fail(e__, #call); } while (0)
+
+struct Guard {
+	int prev = -1;
+	explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+	~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct blight_part_session {
+	const blight_index* idx = nullptr;
+	int device = 0;
+	blight_part_config cfg{};
+	uint64_t region_bytes = 0;
+	// this rank's peer-visible buffers
+	void* inbox = nullptr;     // [2][world sources][cap] records
+	Mailbox* mail = nullptr;
+	int64_t* ids = nullptr;    // id array the owners write into (direct return), ids_capacity entries
+	// the other ranks' buffers as seen from here
+	void* p_inbox[kMaxRanks] = {};
+	Mailbox* p_mail[kMaxRanks] = {};
+	int64_t* p_ids[kMaxRanks] = {};
+	uint64_t p_ids_cap[kMaxRanks] = {};
+	bool ipc_opened[kMaxRanks] = {};
+	uint32_t connected = 0;
+	// local scratch
+	unsigned long long* counts[2] = {nullptr, nullptr};  // as a source: packed counters per owner
+	unsigned long long* rcv[2] = {nullptr, nullptr};     // as an owner: counters received per source
+	uint32_t* err = nullptr;
+	unsigned long long seq = 0;  // sub-batches issued so far (same on every rank: the calls are collective)
+	bool ahead = false;
+};
+
+extern "C" {
+
+int blight_part_session_create(const blight_index* idx, const blight_part_config* cfg, blight_part_session** out) {
+	if (!idx || !cfg || !out) return fail(BL_ERR_INVALID_ARG, "null argument");
+	if (cfg->world == 0 || cfg->world > (uint32_t)kMaxRanks || cfg->rank >= cfg->world) return fail(BL_ERR_INVALID_ARG, "bad world / rank");
+	if (cfg->cap == 0 || cfg->cap >= (1ull << 24)) return fail(BL_ERR_INVALID_ARG, "cap: 1 .. 2^24-1 records per region");
+	if (cfg->sub_positions == 0 || (cfg->sub_positions % kReadsStrip) != 0 || cfg->sub_positions >= (1ull << 32))
+		return fail(BL_ERR_INVALID_ARG, "sub_positions: a multiple of 256 below 2^32");
+	for (uint32_t i = 0; i < cfg->world; i++)
+		if (cfg->cuts[i] > cfg->cuts[i + 1]) return fail(BL_ERR_INVALID_ARG, "cuts must ascend");
+	if (cfg->ids_capacity && !idx->v.pos_id) return fail(BL_ERR_INVALID_ARG, "the id mode of the partitioned path needs the position->id table");
+	Guard g(idx->device);
+	blight_part_session* s = new blight_part_session();
+	s->idx = idx; s->device = idx->device; s->cfg = *cfg;
+	s->region_bytes = cfg->cap * BLIGHT_RUN_RECORD_BYTES;
+	if (const char* e = getenv("BLIGHT_PART_ORDER")) s->ahead = e[0] == 'a';
+	const size_t inbox_bytes = (size_t)2 * cfg->world * s->region_bytes;
+	cudaError_t e = cudaMalloc(&s->inbox, inbox_bytes);
+	if (e == cudaSuccess) e = cudaMemset(s->inbox, 0, inbox_bytes);  // a slot never written must still parse as a (harmless) record
+	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->mail), sizeof(Mailbox));
+	if (e == cudaSuccess) e = cudaMemset(s->mail, 0, sizeof(Mailbox));
+	if (e == cudaSuccess && cfg->ids_capacity) e = cudaMalloc(reinterpret_cast<void**>(&s->ids), (size_t)cfg->ids_capacity * 8);
+	for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+		e = cudaMalloc(reinterpret_cast<void**>(&s->counts[b]), kMaxRanks * 8);
+		if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->rcv[b]), kMaxRanks * 8);
+		if (e == cudaSuccess) e = cudaMemset(s->rcv[b], 0, kMaxRanks * 8);
+	}
+	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->err), 4);
+	if (e == cudaSuccess) e = cudaMemset(s->err, 0, 4);
+	if (e != cudaSuccess) { blight_part_session_free(s); return cu_fail(e, "partition session buffers"); }
+	// a rank is its own peer
+	const uint32_t r = cfg->rank;
+	s->p_inbox[r] = s->inbox; s->p_mail[r] = s->mail; s->p_ids[r] = s->ids; s->p_ids_cap[r] = cfg->ids_capacity;
+	s->connected = 1u << r;
+	*out = s;
+	return BL_OK;
+}
+
+void blight_part_session_free(blight_part_session* s) {
+	if (!s) return;
+	Guard g(s->device);
+	cudaDeviceSynchronize();
+	for (uint32_t r = 0; r < (uint32_t)kMaxRanks; r++)
+		if (s->ipc_opened[r]) {
+			cudaIpcCloseMemHandle(s->p_inbox[r]);
+			cudaIpcCloseMemHandle(s->p_mail[r]);
+			if (s->p_ids[r]) cudaIpcCloseMemHandle(s->p_ids[r]);
+		}
+	cudaFree(s->inbox); cudaFree(s->mail); cudaFree(s->ids);
+	for (int b = 0; b < 2; b++) { cudaFree(s->counts[b]); cudaFree(s->rcv[b]); }
+	cudaFree(s->err);
+	delete s;
+}
+
+int blight_part_session_handles(const blight_part_session* s, unsigned char* handles192) {
+	if (!s || !handles192) return fail(BL_ERR_INVALID_ARG, "null argument");
+	Guard g(s->device);
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+	cudaIpcMemHandle_t h;
+	std::memset(handles192, 0, 192);
+	CU(cudaIpcGetMemHandle(&h, s->inbox));
+	std::memcpy(handles192, &h, 64);
+	CU(cudaIpcGetMemHandle(&h, s->mail));
+	std::memcpy(handles192 + 64, &h, 64);
+	if (s->ids) {
+		CU(cudaIpcGetMemHandle(&h, s->ids));
+		std::memcpy(handles192 + 128, &h, 64);
+	}
+	return BL_OK;
+}
+
+int blight_part_session_connect_ipc(blight_part_session* s, uint32_t peer, const unsigned char* handles192, uint64_t peer_ids_capacity) {
+	if (!s || !handles192) return fail(BL_ERR_INVALID_ARG, "null argument");
+	if (peer >= s->cfg.world || peer == s->cfg.rank) return fail(BL_ERR_INVALID_ARG, "peer rank");
+	Guard g(s->device);
+	cudaIpcMemHandle_t h;
+	void* p = nullptr;
+	std::memcpy(&h, handles192, 64);
+	CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	s->p_inbox[peer] = p;
+	std::memcpy(&h, handles192 + 64, 64);
+	CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	s->p_mail[peer] = static_cast<Mailbox*>(p);
+	if (peer_ids_capacity) {
+		std::memcpy(&h, handles192 + 128, 64);
+		CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		s->p_ids[peer] = static_cast<int64_t*>(p);
+		s->p_ids_cap[peer] = peer_ids_capacity;
+	}
+	s->ipc_opened[peer] = true;
+	s->connected |= 1u << peer;
+	return BL_OK;
+}
+
+int blight_part_session_connect_local(blight_part_session* s, uint32_t peer, const blight_part_session* other) {
+	if (!s || !other) return fail(BL_ERR_INVALID_ARG, "null argument");
+	if (peer >= s->cfg.world || peer == s->cfg.rank || other->cfg.rank != peer) return fail(BL_ERR_INVALID_ARG, "peer rank");
+	if (other->device != s->device) {
+		Guard g(s->device);
+		int can = 0;
+		CU(cudaDeviceCanAccessPeer(&can, s->device, other->device));
+		if (!can) return fail(BL_ERR_CUDA, "no peer access between the two devices");
+		cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+		if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+		else if (e != cudaSuccess) return cu_fail(e, "cudaDeviceEnablePeerAccess");
+	}
+	s->p_inbox[peer] = other->inbox;
+	s->p_mail[peer] = other->mail;
+	s->p_ids[peer] = other->ids;
+	s->p_ids_cap[peer] = other->cfg.ids_capacity;
+	s->connected |= 1u << peer;
+	return BL_OK;
+}
+
+void* blight_part_session_ids(const blight_part_session* s) { return s ? s->ids : nullptr; }
+
+int blight_part_session_query(blight_part_session* s, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
+                              uint64_t n_reads, uint64_t total_bases, uint64_t n_sub, uint64_t* d_ctr, void* stream) {
+	if (!s || !d_ctr || (n_reads && (!d_bases || !d_read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	const blight_part_config& c = s->cfg;
+	if (s->connected != (c.world == 32 ? 0xFFFFFFFFu : ((1u << c.world) - 1u))) return fail(BL_ERR_INVALID_ARG, "not every peer is connected");
+	const bool want_ids = d_kmer_off != nullptr;
+	if (want_ids && !s->ids) return fail(BL_ERR_INVALID_ARG, "the session was created without an id array (ids_capacity)");
+	if (n_sub * c.sub_positions < total_bases) return fail(BL_ERR_INVALID_ARG, "n_sub sub-batches do not cover the reads");
+	Guard g(s->device);
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const uint32_t world = c.world;
+	const long long spin_limit = 60ll * 2000000000ll;  // ~60 s of SM clock
+
+	blight_part_route routes[2];
+	const void* regions[2][kMaxRanks];
+	for (int b = 0; b < 2; b++) {
+		blight_part_route& rt = routes[b];
+		std::memset(&rt, 0, sizeof rt);
+		rt.world = world; rt.rank = c.rank; rt.lb = c.lb; rt.cap = c.cap; rt.kcap = c.sub_positions; rt.side = nullptr;
+		for (uint32_t i = 0; i <= world; i++) rt.cuts[i] = c.cuts[i];
+		for (uint32_t d = 0; d < world; d++) {
+			rt.inbox[d] = static_cast<char*>(s->p_inbox[d]) + ((size_t)b * world + c.rank) * s->region_bytes;  // [half b][source = me] at owner d
+			regions[b][d] = static_cast<const char*>(s->inbox) + ((size_t)b * world + d) * s->region_bytes;   // [half b][source d] here
+		}
+	}
+	MailPtrs mp{};
+	void* out_ids[kMaxRanks];
+	for (uint32_t d = 0; d < world; d++) { mp.m[d] = s->p_mail[d]; out_ids[d] = s->p_ids[d]; }
+
+	auto dispatch = [&](uint64_t i) -> int {
+		const int b = (int)(i & 1);
+		CU(cudaMemsetAsync(s->counts[b], 0, kMaxRanks * 8, st));
+		const uint64_t lo = i * c.sub_positions;
+		if (lo < total_bases && n_reads) {
+			int rc = blight_part_dispatch(s->idx->v.k, s->idx->v.m, d_bases, d_read_off, d_kmer_off, n_reads, total_bases, lo,
+			                              std::min<uint64_t>(total_bases, lo + c.sub_positions), &routes[b],
+			                              reinterpret_cast<uint64_t*>(s->counts[b]), d_ctr, s->err, st);
+			if (rc != BL_OK) return rc;
+		}
+		return BL_OK;
+	};
+	auto publish = [&](uint64_t i) -> int {
+		k_publish_counts<<<1, kMaxRanks, 0, st>>>(mp, s->counts[i & 1], world, c.rank, (uint32_t)(i & 1), s->seq + i + 1);
+		g_launches++;
+		CU(cudaGetLastError());
+		return BL_OK;
+	};
+	auto wait = [&](uint64_t i) -> int {
+		k_wait_counts<<<1, kMaxRanks, 0, st>>>(s->mail, world, (uint32_t)(i & 1), s->seq + i + 1, s->rcv[i & 1], s->err, spin_limit);
+		g_launches++;
+		CU(cudaGetLastError());
+		return BL_OK;
+	};
+	auto lookup = [&](uint64_t i) -> int {
+		const int b = (int)(i & 1);
+		return blight_part_lookup_direct(s->idx, world, regions[b], reinterpret_cast<const uint64_t*>(s->rcv[b]), nullptr,
+		                                 want_ids ? out_ids : nullptr, want_ids ? s->p_ids_cap : nullptr, c.cap, c.sub_positions, d_ctr, st);
+	};
+	int rc = BL_OK;
+#define STEP(x) do { rc = (x); if (rc != BL_OK) return rc; } while (0)
+	if (!s->ahead) {
+		for (uint64_t i = 0; i < n_sub; i++) { STEP(dispatch(i)); STEP(publish(i)); STEP(wait(i)); STEP(lookup(i)); }
+	} else if (n_sub) {
+		STEP(dispatch(0)); STEP(publish(0)); STEP(wait(0));
+		for (uint64_t i = 0; i < n_sub; i++) {
+			if (i + 1 < n_sub) STEP(dispatch(i + 1));
+			STEP(lookup(i));
+			if (i + 1 < n_sub) { STEP(publish(i + 1)); STEP(wait(i + 1)); }
+		}
+	}
+#undef STEP
+	// end-of-batch fence: once every rank's flag is here, every owner has finished its lookups, so the identifiers it stored
+	// into this rank's id array have landed
+	k_publish_counts<<<1, kMaxRanks, 0, st>>>(mp, nullptr, world, c.rank, 2u, s->seq + n_sub + 1);
+	k_wait_counts<<<1, kMaxRanks, 0, st>>>(s->mail, world, 2u, s->seq + n_sub + 1, nullptr, s->err, spin_limit);
+	g_launches += 2;
+	CU(cudaGetLastError());
+	s->seq += n_sub + 1;
+	return BL_OK;
+}
+
+int blight_part_session_status(blight_part_session* s, uint32_t* flags_out, int reset, void* stream) {
+	if (!s || !flags_out) return fail(BL_ERR_INVALID_ARG, "null argument");
+	Guard g(s->device);
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	CU(cudaMemcpyAsync(flags_out, s->err, 4, cudaMemcpyDeviceToHost, st));
+	if (reset) CU(cudaMemsetAsync(s->err, 0, 4, st));
+	CU(cudaStreamSynchronize(st));
+	return BL_OK;
+}
+
+}  // extern "C"

@@ -231,8 +231,9 @@ int stream_file_query(const blight_index* idx, const char* path, uint64_t* ctr) 
 			cudaEventRecord(C.copied[f.buf], cs);
 			cudaEventRecord(C.ev_copy, cs);
 			cudaStreamWaitEvent(st, C.ev_copy, 0);
-			rc = launch_reads(&idx->v, idx->v.k, idx->v.m, C.d_text[s], C.d_off[s], C.d_off[s] + n_rec + 1, nullptr, n_rec, consumed, nullptr, nullptr,
-			                  nullptr, C.d_ctr, st);
+			ReadBatch B;
+			B.d_bases = C.d_text[s]; B.d_read_off = C.d_off[s]; B.d_read_end = C.d_off[s] + n_rec + 1; B.n_reads = n_rec; B.total_bases = consumed;
+			rc = launch_reads(&idx->v, idx->v.k, idx->v.m, B, nullptr, nullptr, nullptr, C.d_ctr, st);
 			if (rc != BL_OK) { rc = fail(rc, std::string("kernel launch failed: ") + g_last_cuda_error); break; }
 			cudaEventRecord(C.done[s], st);
 		} else {

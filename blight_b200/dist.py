@@ -9,10 +9,12 @@ PartitionedSet   large indices: the 2^n MPHF groups are cut into `world` contigu
 
 PartitionedSet has two data paths. `query_reads_fused` is the product on NVLink boxes: the exchange is fused into the
 two kernels either side of it (csrc/part_kernels.cu) — the source stores one 32-byte record per super-k-mer straight into
-the owner's inbox (peer memory), the owner stores ids straight into the source's id buffer; the only collectives are an
-all-to-all of `world` record counts per sub-batch (which is also the barrier) and one all-reduce of the counters per
-batch. `query_reads` is the plain formulation (NCCL all-to-all of (canon, minimizer) out and ids back), kept as the
-fallback when an inbox overflows and as the path the CPU `gloo` tests drive.
+the owner's inbox (peer memory), the owner stores int64 ids straight into the source's id array; the ordering between GPUs
+is device-side flags in peer memory (csrc/part_session.cu), so the only collectives of a batch are the agreement on the
+number of sub-batches and one all-reduce of the counters. `enable_fused(mode="stream")` keeps round 1's variant (32-bit id
+streams + a scatter pass at the source, a counter all-to-all per sub-batch) for comparison. `query_reads` is the plain
+formulation (NCCL all-to-all of (canon, minimizer) out and ids back), kept as the fallback when an inbox overflows and as
+the path the CPU `gloo` tests drive.
 
 The routing (`PartitionPlan`, `exchange_lookup`) is device-agnostic torch code so that world_size-2 `gloo` tests on CPU
 exercise exactly the logic the NCCL path runs; on CUDA the binning and the final scatter are the library's own kernels
@@ -205,6 +207,14 @@ class PartitionedSet:
     # ---- fused path: peer-memory stores inside the kernels -------------------------------------------------------
     def disable_fused(self):
         """Unmaps the peers' buffers, then (after a barrier) frees this rank's."""
+        if getattr(self, "_session", None) is not None:
+            torch.cuda.synchronize()
+            if self._world > 1:
+                dist.barrier(group=self.group)  # nobody may still be storing into this rank's buffers
+            self._session.close()
+            self._session = None
+            self._ids_view = None
+            return
         if not hasattr(self, "_inbox"):
             return
         torch.cuda.synchronize()
@@ -218,16 +228,29 @@ class PartitionedSet:
             self._ret.close()
         del self._inbox, self._ret, self._side
 
-    def enable_fused(self, want_ids: bool = True, sub_positions: int = 64 << 20, records_per_position: Optional[float] = None):
-        """Allocates and exchanges the peer buffers. Per rank, double buffered: an inbox of world regions of `cap` records
-        (written by the sources), and for the id mode a return area of world regions of `sub_positions` 32-bit ids
-        (written by the owners) plus the local side table. sub_positions = base positions per sub-batch (one dispatch,
-        one lookup and one scatter kernel each): at 64 M and 8 ranks that is 2 GB of inbox, 4 GB of return area and 1 GB
-        of side table per rank."""
+    def enable_fused(self, want_ids: bool = True, sub_positions: int = 64 << 20, records_per_position: Optional[float] = None,
+                     ids_capacity: int = 0, mode: Optional[str] = None):
+        """Allocates and exchanges the peer buffers. mode "session" (default): csrc/part_session.cu — per rank a double
+        buffered inbox of world regions of `cap` records (written by the sources), a mailbox of flags, and for the id mode
+        an id array of `ids_capacity` int64 (written by the owners; grown on demand by query_reads_fused). mode "stream":
+        round 1's variant — return area of world regions of `sub_positions` 32-bit ids plus the local side table.
+        sub_positions = base positions per sub-batch (one dispatch and one lookup kernel each)."""
         self.disable_fused()
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         dev = torch.device("cuda", self.index.device)
+        mode = mode or os.environ.get("BLIGHT_PART_RETURN", "session")
+        if mode != "stream":
+            if records_per_position is None:
+                records_per_position = min(0.25, max(0.03, 0.5 / world))
+            max_cap = (1 << 24) - 1
+            sub_positions = min(int(sub_positions), int(max_cap / records_per_position))
+            self._sub = max(256, (sub_positions // 256) * 256)
+            self._cap = min(max(1024, int(self._sub * records_per_position)), max_cap)
+            self._world, self._rank, self._fused_ids = world, rank, want_ids
+            self._session_args = (world, rank)
+            self._make_session(int(ids_capacity) if want_ids else 0)
+            return
         if records_per_position is None:
             # a read batch has ~0.07 super-k-mers per base, spread over `world` owners; an overflow is detected and the
             # batch answered through the plain path, so this only has to be generous, not safe
@@ -294,8 +317,35 @@ class PartitionedSet:
         if world > 1:
             dist.barrier(group=self.group)
 
+    def _make_session(self, ids_capacity: int):
+        """(Re)creates this rank's session with an id array of ids_capacity entries and connects the peers (collective)."""
+        world, rank = self._session_args
+        if getattr(self, "_session", None) is not None:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier(group=self.group)
+            self._session.close()
+        dev = torch.device("cuda", self.index.device)
+        self._session = api.PartSession(self.index, world, rank, self.plan.lb, self.plan.cuts, self._sub, self._cap, ids_capacity)
+        everyone = [None] * world
+        mine = (self._session.handles(), ids_capacity)
+        if world > 1:
+            dist.all_gather_object(everyone, mine, group=self.group)
+        else:
+            everyone = [mine]
+        for r, (h, cap_r) in enumerate(everyone):
+            if r != rank:
+                self._session.connect_ipc(r, h, cap_r)
+        self._ids_view = self._session.ids_tensor(dev)
+        self._err_seen = 0
+        if world > 1:
+            dist.barrier(group=self.group)
+
     def overflowed(self) -> bool:
         """True if the last query_reads_fused on this rank dropped records (only meaningful with check_overflow=False)."""
+        if getattr(self, "_session", None) is not None:
+            self._err_seen |= self._session.status(reset=True)
+            return bool(self._err_seen & api.PART_OVERFLOW)
         return bool(int(self._err.item()))
 
     def query_reads_fused(self, bases: torch.Tensor, read_off: torch.Tensor, kmer_off: Optional[torch.Tensor] = None,
@@ -304,6 +354,8 @@ class PartitionedSet:
         over all ranks). Collective: every rank of the group must call it, with the same want_ids. Per sub-batch i, on the
         current stream: dispatch(i) -> all-to-all of the counters (publishes the records of i and, because every owner
         finished lookup(i-1) before entering it, the ids of i-1) -> scatter(i-1) -> lookup(i)."""
+        if getattr(self, "_session", None) is not None:
+            return self._query_session(bases, read_off, kmer_off, total_kmers, want_ids, ids, check_overflow)
         if not hasattr(self, "_inbox"):
             raise RuntimeError("call enable_fused() first")
         world = self._world
@@ -403,6 +455,52 @@ class PartitionedSet:
                 ids, c = self.query_reads(bases, read_off, kmer_off, total_kmers)
                 return (ids if want_ids else None), all_reduce_counters(c, self.group)
         return (ids[:total_kmers] if want_ids else None), ctr
+
+    def _query_session(self, bases, read_off, kmer_off, total_kmers, want_ids, ids, check_overflow):
+        """query_reads_fused through csrc/part_session.cu. With want_ids the result is a view of the session's id array
+        (valid until the next call) unless the caller passed `ids`, which then receives a copy."""
+        world = self._world
+        dev = bases.device
+        if want_ids and not self._fused_ids:
+            raise ValueError("enable_fused(want_ids=False) was asked for")
+        total = bases.numel()
+        n_sub = (total + self._sub - 1) // self._sub
+        need = int(total_kmers) if want_ids else 0
+        if world > 1:
+            t = torch.tensor([n_sub, need], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            n_sub, need_all = int(t[0].item()), int(t[1].item())
+        else:
+            need_all = need
+        if want_ids and need_all > self._session.ids_capacity:
+            self._make_session(need_all + need_all // 8)  # collective: every rank sees the same maximum
+        ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
+        self._err_seen = 0
+        self._session.query(bases, read_off, kmer_off if want_ids else None, n_sub, ctr)
+        if world > 1:
+            dist.all_reduce(ctr, group=self.group)
+        out = None
+        if want_ids:
+            out = self._ids_view[:total_kmers]
+            if ids is not None:
+                ids[:total_kmers].copy_(out)
+                out = ids[:total_kmers]
+        if check_overflow:
+            flags = torch.tensor([self._session.status(reset=True)], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+            flags = int(flags.item())
+            if int(ctr[api.CTR_INVALID].item()):
+                raise api.InvalidBase(api.ERR_INVALID_BASE, "Invalid char in DNA")  # std::domain_error, kmer.h:68
+            if flags & api.PART_TIMEOUT:
+                raise api.BlightError(api.ERR_CUDA, "partitioned query: a peer's flag never arrived")
+            if flags & api.PART_OVERFLOW:
+                # a region overflowed (far more super-k-mers per base than a read batch has): the plain paths have no such limit
+                if world == 1:
+                    return self.index.query_reads(bases, read_off, kmer_off, total_kmers, want_ids=want_ids)
+                ids2, c = self.query_reads(bases, read_off, kmer_off, total_kmers)
+                return (ids2 if want_ids else None), all_reduce_counters(c, self.group)
+        return out, ctr
 
     def query_kmers(self, canon: torch.Tensor, mini: torch.Tensor) -> torch.Tensor:
         return exchange_lookup(canon, mini, self.plan, lambda c, mn: self.index.query_kmers(c, mini=mn), self.group)

@@ -8,8 +8,8 @@
  * returns until the matching *_free.  "d_" parameters are DEVICE pointers on the index's device and the
  * call is asynchronous on `stream` (a cudaStream_t passed as void*, NULL = legacy default stream);
  * "h_" / unprefixed buffers are host memory and those calls return when the result is in the buffer.
- * Concurrent queries on one index from several host threads are allowed when each uses its own stream
- * (the *_host calls serialise on an internal stream).
+ * Concurrent queries on one index from several host threads are allowed: device-buffer calls when each uses its
+ * own stream, *_host calls always (each takes a context of its own from a pool kept with the index).
  *
  * There is no CPU fallback behind this ABI: every query entry point runs the sm_100a kernels or
  * returns BLIGHT_ERR_NO_DEVICE / BLIGHT_ERR_CUDA.
@@ -138,6 +138,12 @@ int blight_query_reads(const blight_index* idx, const char* d_bases, const uint6
                        const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, uint64_t total_kmers,
                        int64_t* d_ids, uint64_t* d_ctr, void* stream);
 
+/* The same on reads the caller already holds as 2-bit codes: base p of the batch in bits 30 - 2 (p & 15) .. of word p >> 4,
+ * code (c >> 1) & 3 as nuc2int (kmer.h:56-69: A0 C1 T2 G3), first base in the high bits; offsets are base positions as above. */
+int blight_query_reads_packed(const blight_index* idx, const uint32_t* d_packed, const uint64_t* d_read_off,
+                              const uint64_t* d_kmer_off, uint64_t n_reads, uint64_t total_bases, int64_t* d_ids,
+                              uint64_t* d_ctr, void* stream);
+
 /* ---- id consumers fused behind the lookup: what the reference's applications do with the ids of
  * query_sequence_hash, done on the GPU so that ids never leave it. Need the position->id table (N < 2^32-1). ------- */
 #define BLIGHT_CONSUME_COUNT 0 /* d_table[id] += 1 (uint32): `abundance[kmer_ids[i]]++`, Abundance_De_Bruijn_graph_snippet.cpp:132-142
@@ -163,7 +169,10 @@ int blight_query_file_host(const blight_index* idx, const char* path, uint64_t* 
 /* query_sequence_hash(seq): ids_out needs max(0, len-k+1) slots; *n_out receives the count. */
 int blight_query_sequence_host(const blight_index* idx, const char* seq, uint64_t len, int64_t* ids_out,
                                uint64_t* n_out);
-/* Batched form over host reads (no separators; offsets as above); ids_out may be NULL. */
+/* query_sequence_bool(seq), blight.h:129 / blight.cpp:554-571: (Good, Erroneous) of one sequence, counted on the device. */
+int blight_query_sequence_bool_host(const blight_index* idx, const char* seq, uint64_t len, uint64_t* found, uint64_t* not_found);
+/* Batched form over host reads (no separators; offsets as above); ids_out may be NULL. Large batches cross PCIe partly as
+ * ASCII and partly 2-bit packed by the host cores (csrc/host_query.cu); BLIGHT_HOST_PACK=0 / BLIGHT_HOST_THREADS=n tune it. */
 int blight_query_reads_host(const blight_index* idx, const char* bases, const uint64_t* read_off, uint64_t n_reads,
                             int64_t* ids_out, uint64_t* ctr);
 /* query_kmer_hash over a host array of canonical k-mers. */
@@ -221,6 +230,46 @@ int blight_part_lookup(const blight_index* idx, uint32_t world, const void* cons
  * blight_info.id_base of owner d's index; NULL = all zero) is added back here. */
 int blight_part_scatter(const void* d_side, uint64_t cap, const uint64_t* d_counts, const void* d_ret, uint64_t kcap, uint32_t world,
                         uint64_t max_records, const uint64_t* id_bases, int64_t* d_ids, void* stream);
+/* blight_part_lookup with the identifiers returned DIRECTLY: out_ids[s] = source s's int64 id array (peer pointer),
+ * out_caps[s] its length; the records must come from a dispatch whose route had side == NULL and d_kmer_off != NULL (they
+ * then carry the slot of each run's first k-mer in that array). ret must be NULL. No scatter pass follows. */
+int blight_part_lookup_direct(const blight_index* idx, uint32_t world, const void* const* regions, const uint64_t* d_counts,
+                              void* const* ret, void* const* out_ids, const uint64_t* out_caps, uint64_t cap, uint64_t kcap,
+                              uint64_t* d_ctr, void* stream);
+
+/* ---- one rank of the partitioned path as an object: buffers, peers, and the per-batch pipeline, with the ordering between
+ * GPUs done by device-side flags in peer memory (no collective call on the data path). The ranks are processes (exchange the
+ * handles, connect_ipc) or devices of one process (connect_local). ------------------------------------------------------ */
+typedef struct blight_part_session blight_part_session;
+typedef struct blight_part_config {
+	uint32_t world, rank;
+	uint32_t lb;                         /* log2(buckets per MPHF group) */
+	uint32_t reserved;
+	uint32_t cuts[BLIGHT_MAX_RANKS + 1]; /* rank r owns MPHF groups [cuts[r], cuts[r+1]) */
+	uint64_t sub_positions;              /* base positions per sub-batch (multiple of 256, < 2^32) */
+	uint64_t cap;                        /* records per (source, owner) inbox region and sub-batch (< 2^24) */
+	uint64_t ids_capacity;               /* entries of this rank's id array (0: counting mode only) */
+} blight_part_config;
+#define BLIGHT_PART_OVERFLOW 1u /* status flag: an inbox region was too small, records were dropped (answer the batch another way) */
+#define BLIGHT_PART_TIMEOUT 2u  /* status flag: a peer's flag never arrived */
+int blight_part_session_create(const blight_index* local_slice, const blight_part_config* cfg, blight_part_session** out);
+void blight_part_session_free(blight_part_session* s);
+/* 3 x 64 bytes: CUDA IPC handles of this rank's inbox, mailbox and id array (zeros when there is none). */
+int blight_part_session_handles(const blight_part_session* s, unsigned char* handles192);
+int blight_part_session_connect_ipc(blight_part_session* s, uint32_t peer, const unsigned char* handles192, uint64_t peer_ids_capacity);
+int blight_part_session_connect_local(blight_part_session* s, uint32_t peer, const blight_part_session* other);
+/* DEVICE pointer of this rank's id array: after a query (and a synchronisation of its stream) slot d_kmer_off[r] + pos holds
+ * the identifier query_sequence_hash would return for k-mer pos of read r (blight.cpp:575-591). */
+void* blight_part_session_ids(const blight_part_session* s);
+/* One batch of reads held by THIS rank, collective: every rank calls it with the same n_sub (>= ceil(total_bases /
+ * sub_positions) of every rank) and the same mode (d_kmer_off NULL everywhere = counting). Asynchronous on `stream`.
+ * d_ctr accumulates QUERIES / INVALID for this rank's reads and FOUND / NOT_FOUND for the k-mers this rank OWNS: sum the
+ * counters over the ranks. When the stream has drained, every identifier of this rank's reads is in its id array. */
+int blight_part_session_query(blight_part_session* s, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
+                              uint64_t n_reads, uint64_t total_bases, uint64_t n_sub, uint64_t* d_ctr, void* stream);
+/* BLIGHT_PART_* flags raised since the last reset (synchronises `stream`). */
+int blight_part_session_status(blight_part_session* s, uint32_t* flags_out, int reset, void* stream);
+
 /* Device buffers other processes of the box can map (CUDA IPC): alloc + 64-byte handle here, open there. */
 int blight_peer_alloc(uint64_t bytes, void** d_ptr, unsigned char* handle64);
 int blight_peer_open(const unsigned char* handle64, void** d_ptr);
@@ -233,6 +282,8 @@ int blight_peer_free(void* d_ptr);
 int blight_fasta_cut_stream(const char* text, uint64_t len, uint64_t chunk_bytes, uint64_t* beg_out, uint64_t* end_out,
                             uint64_t cap, uint64_t* n_out);
 
+/* Bytes the host-buffer entry points copied host->device and device->host in the calling process since load. */
+void blight_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
 /* Number of kernel launches issued by this library in the calling process (all threads) since load. */
 uint64_t blight_launch_count(void);
 

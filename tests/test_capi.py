@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_header_symbols_are_exported():
     hdr = open(os.path.join(ROOT, "include", "blight_b200.h")).read()
-    declared = sorted(set(re.findall(r"^(?:int|void|uint64_t|const char\*)\s+(blight_[a-z_0-9]+)\s*\(", hdr, re.M)))
+    declared = sorted(set(re.findall(r"^(?:int|void\*?|uint64_t|const char\*)\s+(blight_[a-z_0-9]+)\s*\(", hdr, re.M)))
     assert declared, "no declarations parsed"
     L = api.lib()
     for name in declared:

@@ -26,9 +26,13 @@ def _dev_batch(torch, rb, ro, k=31):
             torch.from_numpy(koff.astype(np.int64)).cuda(), int(koff[-1]))
 
 
+@pytest.mark.parametrize("mode", ["session", "stream"])
 @pytest.mark.parametrize("shape", [(9, 6, 6), (7, 5, 0), (11, 8, 8)])
-def test_loopback_partition_matches_oracle(shape, tmp_path, torch_cuda, monkeypatch):
+def test_loopback_partition_matches_oracle(shape, mode, tmp_path, torch_cuda, monkeypatch):
+    """mode session: ids stored straight into the source's id array, ordering by device-side flags (part_session.cu);
+    mode stream: round 1's 32-bit return streams + scatter pass."""
     torch = torch_cuda
+    monkeypatch.setenv("BLIGHT_PART_RETURN", mode)
     m, n, b = shape
     g, ub, uo, rb, ro = common.synthetic(600_000, 6000, seed=11 + m, sub_rate=0.03)
     flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=m, n=n, s=0, b=b, threads=0)
@@ -50,6 +54,7 @@ def test_loopback_partition_matches_oracle(shape, tmp_path, torch_cuda, monkeypa
     assert torch.equal(ctr2.cpu(), ctr.cpu())
     # the experimental kernel order (dispatch of the next sub-batch ahead of the lookup of this one): same answers
     monkeypatch.setenv("BLIGHT_PART_ORDER", "ahead")
+    ps.enable_fused(sub_positions=1 << 17)  # the order is read when the buffers are set up
     ids3, ctr3 = ps.query_reads_fused(d_b, d_o, d_k, total)
     torch.cuda.synchronize()
     assert np.array_equal(ids3.cpu().numpy(), want) and torch.equal(ctr3.cpu(), ctr.cpu())
@@ -145,3 +150,65 @@ def test_three_owners_two_sources_on_one_gpu(tmp_path, torch_cuda):
     for s in range(2):
         assert np.array_equal(ids_bufs[s].cpu().numpy(), parts[s][2]), s
     assert (int(ctr[0]), int(ctr[1]), int(ctr[2])) == (int(wctr[0]), int(wctr[1]), int(wctr[2]))
+
+
+def test_three_sessions_on_one_gpu(tmp_path, torch_cuda, monkeypatch):
+    """Three ranks of the partitioned path as three sessions of ONE process on GPU 0 (connect_local, one stream each): the
+    ordering between ranks is nothing but the device-side flags, exactly as between the GPUs of a box. Ranks hold unequal
+    shares of the reads (one holds none); ids land in each rank's own id array; both kernel orders."""
+    torch = torch_cuda
+    m, n, b, world = 9, 8, 6, 3
+    g, ub, uo, rb, ro = common.synthetic(800_000, 9000, seed=29, sub_rate=0.02)
+    flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=m, n=n, s=0, b=b, threads=0)
+    port = common.cport_of(flat, tmp_path)
+    want, wctr = port.query_reads(rb, ro)
+    plan = bdist.PartitionPlan.balanced(flat.group_sizes(), world, 2 * m - 1 - n)
+    owners = [flat.slice(*plan.group_range(r)).upload(0) for r in range(world)]
+    koff_all = synth.kmer_offsets(ro, 31)
+    cutsr = [0, 6000, 9000, 9000]  # reads per rank: 6000, 3000, 0
+    for order in ("", "ahead"):
+        monkeypatch.setenv("BLIGHT_PART_ORDER", order)
+        sub = 1 << 17
+        sess, batches = [], []
+        for r in range(world):
+            lo, hi = cutsr[r], cutsr[r + 1]
+            pb = rb[int(ro[lo]):int(ro[hi])] if hi > lo else np.zeros(0, dtype=np.uint8)
+            po = (ro[lo:hi + 1] - ro[lo]) if hi > lo else np.zeros(1, dtype=np.uint64)
+            d_b, d_o, d_k, total = _dev_batch(torch, pb, po)
+            batches.append((d_b, d_o, d_k, total, want[int(koff_all[lo]):int(koff_all[hi])]))
+            sess.append(api.PartSession(owners[r], world, r, plan.lb, plan.cuts, sub, 1 << 15, max(total, 1)))
+        for r in range(world):
+            for q in range(world):
+                if q != r:
+                    sess[r].connect_local(q, sess[q])
+        n_sub = max((bt[0].numel() + sub - 1) // sub for bt in batches)
+        streams = [torch.cuda.Stream() for _ in range(world)]
+        ctrs = [torch.zeros(api.N_CTR, dtype=torch.int64, device="cuda") for _ in range(world)]
+        torch.cuda.synchronize()
+        for rep in range(2):  # twice: the sequence numbers carry over between batches
+            for r in range(world):
+                ctrs[r].zero_()
+            torch.cuda.synchronize()
+            for r in range(world):
+                d_b, d_o, d_k, total, _ = batches[r]
+                sess[r].query(d_b, d_o, d_k, n_sub, ctrs[r], stream=streams[r])
+            torch.cuda.synchronize()
+            for r in range(world):
+                assert sess[r].status(stream=streams[r]) == 0
+                total, w = batches[r][3], batches[r][4]
+                got = sess[r].ids_tensor("cuda")[:total].cpu().numpy()
+                assert np.array_equal(got, w), (order, rep, r)
+            tot = sum(c.cpu().numpy() for c in ctrs)
+            assert (int(tot[0]), int(tot[1]), int(tot[2])) == (int(wctr[0]), int(wctr[1]), int(wctr[2]))
+        # counting mode
+        for r in range(world):
+            ctrs[r].zero_()
+        torch.cuda.synchronize()
+        for r in range(world):
+            d_b, d_o, d_k, total, _ = batches[r]
+            sess[r].query(d_b, d_o, None, n_sub, ctrs[r], stream=streams[r])
+        torch.cuda.synchronize()
+        tot = sum(c.cpu().numpy() for c in ctrs)
+        assert (int(tot[0]), int(tot[1]), int(tot[2])) == (int(wctr[0]), int(wctr[1]), int(wctr[2]))
+        for s_ in sess:
+            s_.close()
