@@ -30,7 +30,9 @@ SYMBOLS = [
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
     "blight_consume_reads", "blight_gather_reads", "blight_fasta_cut_stream", "blight_part_dispatch", "blight_part_lookup", "blight_part_lookup_direct", "blight_part_scatter",
     "blight_part_session_create", "blight_part_session_free", "blight_part_session_handles", "blight_part_session_connect_ipc",
-    "blight_part_session_connect_local", "blight_part_session_ids", "blight_part_session_query", "blight_part_session_status", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
+    "blight_part_session_connect_local", "blight_part_session_ids", "blight_part_session_query", "blight_part_session_status",
+    "blight_comm_init", "blight_comm_free", "blight_comm_describe", "blight_comm_query_reads_host", "blight_comm_query_fasta_host",
+    "blight_comm_query_file_host", "blight_comm_query_sequence_host", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
 ]
 MAX_RANKS = 16
 RUN_RECORD_BYTES = 32
@@ -73,6 +75,13 @@ class Info(C.Structure):
 
 
 LAYOUT_POS_ID, LAYOUT_FILTER, LAYOUT_EXACT_POS = 1, 2, 4
+COMM_REPLICA, COMM_PARTITION = 0, 1
+
+
+class CommInfo(C.Structure):
+    """blight_comm_info (include/blight_b200.h)"""
+    _fields_ = [("n_gpus", C.c_uint32), ("mode", C.c_uint32), ("devices", C.c_int32 * MAX_RANKS), ("device_bytes", C.c_uint64 * MAX_RANKS),
+                ("kmers", C.c_uint64 * MAX_RANKS), ("cuts", C.c_uint32 * (MAX_RANKS + 1)), ("whole", Info)]
 
 
 class UploadOptions(C.Structure):
@@ -155,6 +164,14 @@ def lib() -> C.CDLL:
     L.blight_part_session_ids.restype = vp
     L.blight_part_session_query.argtypes = [vp, vp, vp, vp, u64, u64, u64, vp, vp]
     L.blight_part_session_status.argtypes = [vp, C.POINTER(u32), C.c_int, vp]
+    L.blight_comm_init.argtypes = [vp, C.POINTER(C.c_int), u32, C.c_int, vp, C.POINTER(vp)]
+    L.blight_comm_free.argtypes = [vp]
+    L.blight_comm_free.restype = None
+    L.blight_comm_describe.argtypes = [vp, C.POINTER(CommInfo)]
+    L.blight_comm_query_reads_host.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.blight_comm_query_fasta_host.argtypes = [vp, vp, u64, vp]
+    L.blight_comm_query_file_host.argtypes = [vp, cp, vp]
+    L.blight_comm_query_sequence_host.argtypes = [vp, vp, u64, vp, C.POINTER(u64)]
     L.blight_peer_alloc.argtypes = [u64, C.POINTER(vp), C.c_char_p]
     L.blight_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.blight_peer_close.argtypes = [vp]
@@ -417,6 +434,66 @@ class DeviceIndex:
         if getattr(self, "_h", None) and self._h.value and _lib is not None:
             _lib.blight_index_free(self._h)
             self._h = C.c_void_p()
+
+
+class Comm:
+    """Several GPUs of the box driven from this process (blight_comm, csrc/comm.cu): replica or bucket-partitioned; the
+    host-buffer queries of a DeviceIndex with the same results."""
+
+    def __init__(self, flat: FlatIndex, devices: Sequence[int], mode: int = COMM_REPLICA, options: Optional[UploadOptions] = None):
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(lib().blight_comm_init(flat._h, devs, len(devices), mode, C.addressof(options) if options is not None else None, C.byref(h)))
+        self._h = h
+        ci = CommInfo()
+        _check(lib().blight_comm_describe(self._h, C.byref(ci)))
+        self.k = int(ci.whole.k)
+        self.n_gpus, self.mode = int(ci.n_gpus), int(ci.mode)
+        self.cuts = [int(ci.cuts[i]) for i in range(self.n_gpus + 1)]
+        self.device_bytes = [int(ci.device_bytes[i]) for i in range(self.n_gpus)]
+        self.kmers = [int(ci.kmers[i]) for i in range(self.n_gpus)]
+
+    def query_reads_host(self, bases: np.ndarray, read_off: np.ndarray, want_ids=True):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        ids = None
+        if want_ids:
+            lens = np.diff(read_off.astype(np.int64))
+            ids = np.empty(int(np.maximum(lens - (self.k - 1), 0).sum()), dtype=np.int64)
+        ctr = np.zeros(N_CTR, dtype=np.uint64)
+        _check(lib().blight_comm_query_reads_host(self._h, bases.ctypes.data, read_off.ctypes.data, len(read_off) - 1, _ptr(ids), ctr.ctypes.data))
+        return ids, ctr
+
+    def query_fasta_host(self, text) -> np.ndarray:
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        ctr = np.zeros(N_CTR, dtype=np.uint64)
+        _check(lib().blight_comm_query_fasta_host(self._h, _ptr(buf), len(buf), ctr.ctypes.data))
+        return ctr
+
+    def query_file_host(self, path: str) -> np.ndarray:
+        ctr = np.zeros(N_CTR, dtype=np.uint64)
+        _check(lib().blight_comm_query_file_host(self._h, os.fsencode(path), ctr.ctypes.data))
+        return ctr
+
+    def query_sequence_host(self, seq) -> np.ndarray:
+        if isinstance(seq, str):
+            seq = seq.encode()
+        buf = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        out = np.empty(max(len(buf) - self.k + 1, 0), dtype=np.int64)
+        n = C.c_uint64()
+        _check(lib().blight_comm_query_sequence_host(self._h, buf.ctypes.data, len(buf), out.ctypes.data, C.byref(n)))
+        return out[:n.value]
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.blight_comm_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PeerBuffer:

@@ -64,6 +64,9 @@ int launch_reads_sink(const DevIndexView& I, int kind, const ReadBatch& B, uint3
 int part_dispatch_batch(uint32_t k, uint32_t m, const ReadBatch& B, uint64_t pos_begin, uint64_t pos_end, const ::blight_part_route* route,
                         uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream);
 
+// part_session.cu: blight_part_session_query on a ReadBatch (records with explicit ends, packed text)
+int part_session_query_batch(::blight_part_session* s, const ReadBatch& B, uint64_t n_sub, uint64_t* d_ctr, void* stream);
+
 // Start positions are handled in strips of this many bases; pos_begin of a partial launch must be a multiple of it.
 constexpr uint64_t kReadsStrip = 256;
 

@@ -221,7 +221,19 @@ void* blight_part_session_ids(const blight_part_session* s) { return s ? s->ids 
 
 int blight_part_session_query(blight_part_session* s, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
                               uint64_t n_reads, uint64_t total_bases, uint64_t n_sub, uint64_t* d_ctr, void* stream) {
-	if (!s || !d_ctr || (n_reads && (!d_bases || !d_read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
+	ReadBatch B;
+	B.d_bases = d_bases; B.d_read_off = d_read_off; B.d_kmer_off = d_kmer_off; B.n_reads = n_reads; B.total_bases = total_bases;
+	return part_session_query_batch(s, B, n_sub, d_ctr, stream);
+}
+
+}  // extern "C"
+
+int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB, uint64_t n_sub, uint64_t* d_ctr, void* stream) {
+	const char* d_bases = RB.d_bases;
+	const uint64_t* d_read_off = RB.d_read_off;
+	const uint64_t* d_kmer_off = RB.d_kmer_off;
+	const uint64_t n_reads = RB.n_reads, total_bases = RB.total_bases;
+	if (!s || !d_ctr || (n_reads && ((!d_bases && !RB.d_packed) || !d_read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
 	const blight_part_config& c = s->cfg;
 	if (s->connected != (c.world == 32 ? 0xFFFFFFFFu : ((1u << c.world) - 1u))) return fail(BL_ERR_INVALID_ARG, "not every peer is connected");
 	const bool want_ids = d_kmer_off != nullptr;
@@ -253,9 +265,8 @@ int blight_part_session_query(blight_part_session* s, const char* d_bases, const
 		CU(cudaMemsetAsync(s->counts[b], 0, kMaxRanks * 8, st));
 		const uint64_t lo = i * c.sub_positions;
 		if (lo < total_bases && n_reads) {
-			int rc = blight_part_dispatch(s->idx->v.k, s->idx->v.m, d_bases, d_read_off, d_kmer_off, n_reads, total_bases, lo,
-			                              std::min<uint64_t>(total_bases, lo + c.sub_positions), &routes[b],
-			                              reinterpret_cast<uint64_t*>(s->counts[b]), d_ctr, s->err, st);
+			int rc = part_dispatch_batch(s->idx->v.k, s->idx->v.m, RB, lo, std::min<uint64_t>(total_bases, lo + c.sub_positions), &routes[b],
+			                             reinterpret_cast<uint64_t*>(s->counts[b]), d_ctr, s->err, st);
 			if (rc != BL_OK) return rc;
 		}
 		return BL_OK;
@@ -299,6 +310,8 @@ int blight_part_session_query(blight_part_session* s, const char* d_bases, const
 	s->seq += n_sub + 1;
 	return BL_OK;
 }
+
+extern "C" {
 
 int blight_part_session_status(blight_part_session* s, uint32_t* flags_out, int reset, void* stream) {
 	if (!s || !flags_out) return fail(BL_ERR_INVALID_ARG, "null argument");

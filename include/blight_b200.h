@@ -276,6 +276,34 @@ int blight_peer_open(const unsigned char* handle64, void** d_ptr);
 int blight_peer_close(void* d_ptr);
 int blight_peer_free(void* d_ptr);
 
+/* ---- several GPUs of one box from ONE process: what a kmer_Set_Light drop-in holds instead of a single
+ * blight_index when it is given more than one device. REPLICA: the whole index per device, a batch's reads cut into one
+ * share per device (BASELINE configs[3]). PARTITION: MPHF groups cut into one contiguous range per device (balanced by
+ * k-mer count; needs 2^n_log2 >= devices), super-k-mers routed to the owner of their minimizer bucket and identifiers
+ * returned over NVLink by the kernels themselves (BASELINE configs[4]). Results are those of a single device holding the
+ * whole index, identifier for identifier. A device may be listed more than once (tests on a one-GPU box). ------------- */
+typedef struct blight_comm blight_comm;
+#define BLIGHT_COMM_REPLICA 0
+#define BLIGHT_COMM_PARTITION 1
+typedef struct blight_comm_info {
+	uint32_t n_gpus, mode;
+	int32_t devices[BLIGHT_MAX_RANKS];
+	uint64_t device_bytes[BLIGHT_MAX_RANKS]; /* HBM held per device */
+	uint64_t kmers[BLIGHT_MAX_RANKS];        /* k-mers indexed per device (PARTITION: the slice; REPLICA: all) */
+	uint32_t cuts[BLIGHT_MAX_RANKS + 1];     /* PARTITION: device g owns MPHF groups [cuts[g], cuts[g+1]) */
+	blight_info whole;                       /* the index as a whole */
+} blight_comm_info;
+int blight_comm_init(const blight_flat* f, const int* devices, uint32_t n_gpus, int mode, const blight_upload_options* opts,
+                     blight_comm** out);
+void blight_comm_free(blight_comm* c);
+int blight_comm_describe(const blight_comm* c, blight_comm_info* out);
+/* The host-buffer entry points of a single index, spread over the devices (same arguments, same results). */
+int blight_comm_query_reads_host(blight_comm* c, const char* bases, const uint64_t* read_off, uint64_t n_reads, int64_t* ids_out,
+                                 uint64_t* ctr);
+int blight_comm_query_fasta_host(blight_comm* c, const char* text, uint64_t len, uint64_t* ctr);
+int blight_comm_query_file_host(blight_comm* c, const char* path, uint64_t* ctr);
+int blight_comm_query_sequence_host(blight_comm* c, const char* seq, uint64_t len, int64_t* ids_out, uint64_t* n_out);
+
 /* Test hook: the record cut of the streaming file_query (chunks of chunk_bytes, the unfinished tail carried over)
  * applied to a text in memory; records = sequence lines [beg, end) as file offsets, the reference's pairing rules
  * (blight.cpp:760-772). *n_out = records found (may exceed cap; only the first cap are stored). */

@@ -33,6 +33,12 @@ int main(int argc, char** argv) {
 		return 0;
 	}
 	kmer_Set_Light ksl(31, 7, 5, 3, 4, 6);
+	if (argc > 4) {
+		// several devices from one process: argv[3] = replica | partition, argv[4..] = device ordinals (repeats allowed)
+		std::vector<int> devs;
+		for (int i = 4; i < argc; i++) devs.push_back(std::stoi(argv[i]));
+		ksl.use_devices(devs, std::string(argv[3]) == "partition" ? BLIGHT_COMM_PARTITION : BLIGHT_COMM_REPLICA);
+	}
 	ksl.construct_index(fasta);
 	std::cout << "number_kmer " << ksl.number_kmer << "\nnumber_super_kmer " << ksl.number_super_kmer << "\n";
 	std::ifstream in(fasta);

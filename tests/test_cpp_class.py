@@ -44,12 +44,23 @@ def test_class_exceptions_without_a_gpu(tmp_path):
         assert f[key] == "1", (key, r.stdout)
 
 
+def _devices(n_sim=3):
+    """Every GPU of the box, or GPU 0 listed n_sim times on a one-GPU box (the ranks are then separate indices / sessions
+    on one device: same code, same flags, no NVLink)."""
+    import torch
+    n = torch.cuda.device_count()
+    return [str(i) for i in range(n)] if n > 1 else ["0"] * n_sim
+
+
 @pytest.mark.gpu
-def test_class_on_lambda(tmp_path):
+@pytest.mark.parametrize("comm", [None, "replica", "partition"])
+def test_class_on_lambda(tmp_path, comm):
+    """comm None: one device. replica / partition: the same object spread over several devices by ONE process
+    (kmer_Set_Light::use_devices -> blight_comm, csrc/comm.cu): every fact must be unchanged."""
     exe = _build(tmp_path)
     fa = tmp_path / "lambda.fa"
     fa.write_bytes(fixtures.lambda_fasta())
-    r = subprocess.run([exe, "gpu", str(fa)], capture_output=True, text=True)
+    r = subprocess.run([exe, "gpu", str(fa)] + ([comm] + _devices() if comm else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     f = _facts(r.stdout)
     for key in ("invalid_even_m", "invalid_big_n", "valid_params", "query_before_index", "missing_file", "short_read_empty",
