@@ -394,23 +394,31 @@ def partition_leg(args, rank, world, local, dev):
     scratch = torch.empty(total, dtype=torch.int64, device=dev)
     one_ids_ms = timed(lambda: whole.query_reads(bases, roff, koff, total, ids=scratch))
     one_cnt_ms = timed(lambda: whole.query_reads(bases, roff, want_ids=False))
-    del scratch
     whole_bytes = whole.info["device_bytes"]
 
-    part.enable_fused(sub_positions=args.partition_sub, ids_capacity=total)
-    ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
-    torch.cuda.synchronize()
-    same = torch.tensor([1 if torch.equal(ids_f, ids_one) else 0], device=dev)
-    dist.all_reduce(same, op=dist.ReduceOp.MIN)
-    _, ctr_c = part.query_reads_fused(bases, roff, want_ids=False)
-    torch.cuda.synchronize()
-    ctr_ok = bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]) and torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
+    del scratch
+    variants, same_all, ctr_ok_all, ovf_all = {}, True, True, False
+    for order in ("serial", "ahead", "overlap"):
+        part.enable_fused(sub_positions=args.partition_sub, ids_capacity=total, order=order)
+        ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
+        torch.cuda.synchronize()
+        same = torch.tensor([1 if torch.equal(ids_f, ids_one) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        _, ctr_c = part.query_reads_fused(bases, roff, want_ids=False)
+        torch.cuda.synchronize()
+        ctr_ok = bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]) and torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
+        f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, check_overflow=False))
+        f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False))
+        ovf = torch.tensor([1 if part.overflowed() else 0], device=dev)
+        dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
+        variants[order] = {"ids_ms": f_ids_ms, "counting_ms": f_cnt_ms, "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms,
+                           "counting_vs_one_gpu": world * one_cnt_ms / f_cnt_ms, "ids_equal_replica": bool(same.item()),
+                           "counters_equal_replica": ctr_ok, "overflow": bool(ovf.item())}
+        same_all &= bool(same.item()); ctr_ok_all &= ctr_ok; ovf_all |= bool(ovf.item())
     del ids_one, whole
     torch.cuda.empty_cache()
-    f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, check_overflow=False))
-    f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False))
-    ovf = torch.tensor([1 if part.overflowed() else 0], device=dev)
-    dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
+    default_order = bdist.DEFAULT_ORDER
+    f_ids_ms, f_cnt_ms = variants[default_order]["ids_ms"], variants[default_order]["counting_ms"]
     local_bytes = part.index.info["device_bytes"]
     part.disable_fused()
     dist.barrier()
@@ -425,9 +433,10 @@ def partition_leg(args, rank, world, local, dev):
         "one_gpu_whole_index": {"ids": total / (one_ids_ms * 1e-3), "counting": total / (one_cnt_ms * 1e-3), "unit": "k-mers/s",
                                 "ids_ms": one_ids_ms, "counting_ms": one_cnt_ms, "device_bytes": whole_bytes},
         "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms, "counting_vs_one_gpu": world * one_cnt_ms / f_cnt_ms,
-        "ids_equal_replica": bool(same.item()), "counters_equal_replica": ctr_ok, "overflow": bool(ovf.item()),
+        "ids_equal_replica": same_all, "counters_equal_replica": ctr_ok_all, "overflow": ovf_all,
+        "kernel_order": default_order, "by_kernel_order": variants,
         "device_bytes_per_gpu": local_bytes, "cuts": part.plan.cuts, "sub_positions": part._sub,
-        "return_path": os.environ.get("BLIGHT_PART_RETURN", "session") + ("+ahead" if os.environ.get("BLIGHT_PART_ORDER") == "ahead" else ""),
+        "return_path": "ids stored by the owner straight into the source's int64 id array; ordering between GPUs by device-side flags (csrc/part_session.cu)",
         "build_seconds": build_s, "leg_seconds": time.time() - t_leg,
     }
 

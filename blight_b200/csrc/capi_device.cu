@@ -211,6 +211,7 @@ int blight_index_upload_opts(const blight_flat* ff, int device, const blight_upl
 	v.fb_vals = static_cast<const uint64_t*>(idx->d_fbv);
 	v.k = H.k; v.m = H.m; v.b = H.b; v.lb = F.lb();
 	v.kmask = (1ull << (2 * H.k)) - 1;
+	if (const char* e = getenv("BLIGHT_FORCE_WIDE")) { if (atoi(e)) small = 0; }  // test knob: the 64-bit bit arithmetic of huge MPHF groups
 	v.small = small;
 	if (exact) v.flags |= kFlagExactPos;
 	{

@@ -149,16 +149,27 @@ int partition_batch(blight_comm* c, const char* text, const uint64_t* beg, const
 	const uint64_t n_sub = std::max<uint64_t>(1, (max_len + c->sub - 1) / c->sub);
 	std::vector<uint64_t> ctrs((size_t)W * BLIGHT_N_CTR, 0);
 	std::vector<uint32_t> flags(W, 0);
+	// Phase 1, every rank: allocations only. cudaMalloc waits for the device to drain (and, with peer access, touches the
+	// peers): it must never run while another rank's wait kernel is spinning on a flag this rank has yet to publish.
 	int rc = for_each_rank(W, [&](uint32_t g) -> int {
 		cudaSetDevice(c->devices[g]);
 		RankWs& w = c->ws[g];
 		if (!w.st) CU(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
 		const uint64_t r0 = r_cut[g], r1 = r_cut[g + 1], cnt = r1 - r0;
-		const uint64_t t0 = beg[r0], len = cnt ? (end ? end[r1 - 1] : beg[r1]) - t0 : 0;
+		const uint64_t len = cnt ? (end ? end[r1 - 1] : beg[r1]) - beg[r0] : 0;
 		int rc2;
 		if ((rc2 = w.reserve(0, len + 64)) != BL_OK) return rc2;
 		if ((rc2 = w.reserve(1, (cnt + 1) * 8 * 3 + 64)) != BL_OK) return rc2;
-		if ((rc2 = w.reserve(2, BLIGHT_N_CTR * 8)) != BL_OK) return rc2;
+		return w.reserve(2, BLIGHT_N_CTR * 8);
+	});
+	if (rc != BL_OK) return rc;
+	// Phase 2: copies, the collective pipeline, results. Nothing below allocates.
+	rc = for_each_rank(W, [&](uint32_t g) -> int {
+		cudaSetDevice(c->devices[g]);
+		RankWs& w = c->ws[g];
+		const uint64_t r0 = r_cut[g], r1 = r_cut[g + 1], cnt = r1 - r0;
+		const uint64_t t0 = beg[r0], len = cnt ? (end ? end[r1 - 1] : beg[r1]) - t0 : 0;
+		int rc2;
 		uint64_t* d_beg = static_cast<uint64_t*>(w.p[1]);
 		uint64_t* d_end = d_beg + cnt + 1;
 		uint64_t* d_koff = d_end + cnt + 1;

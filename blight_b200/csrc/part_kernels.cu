@@ -32,6 +32,7 @@
 #include "lookup.cuh"
 
 namespace blight {
+thread_local int g_part_blocks_per_sm = 0;
 namespace {
 
 constexpr int kMaxRanks = BLIGHT_MAX_RANKS;
@@ -536,6 +537,9 @@ int per_sm(K kernel) {
 	return nb;
 }
 
+// resident CTAs per SM a launch may take: what fits, unless the caller shares the SMs between two kernels (part_session.cu)
+int limit_per_sm(int fits) { return g_part_blocks_per_sm > 0 && g_part_blocks_per_sm < fits ? g_part_blocks_per_sm : fits; }
+
 struct DeviceGuardLite {
 	int prev = -1;
 	explicit DeviceGuardLite(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -593,12 +597,12 @@ int part_dispatch_batch(uint32_t k, uint32_t m, const ReadBatch& B, uint64_t pos
 	const double rpb = B.rpb > 0 ? B.rpb : (double)n_reads / (double)total_bases;
 	if (B.d_kmer_off) {
 		static const int nb = per_sm(k_dispatch_runs<true>);
-		const uint64_t cap = (uint64_t)sm_count_() * nb;
+		const uint64_t cap = (uint64_t)sm_count_() * limit_per_sm(nb);
 		k_dispatch_runs<true><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(k, m, B.d_bases, B.d_read_off, B.d_read_end, B.d_kmer_off, n_reads,
 			total_bases, strip_lo, strip_hi, al, B.d_packed, rpb, B.guess_p0, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err);
 	} else {
 		static const int nb = per_sm(k_dispatch_runs<false>);
-		const uint64_t cap = (uint64_t)sm_count_() * nb;
+		const uint64_t cap = (uint64_t)sm_count_() * limit_per_sm(nb);
 		k_dispatch_runs<false><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(k, m, B.d_bases, B.d_read_off, B.d_read_end, nullptr, n_reads,
 			total_bases, strip_lo, strip_hi, al, B.d_packed, rpb, B.guess_p0, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err);
 	}
@@ -641,7 +645,7 @@ int blight_part_lookup_direct(const blight_index* idx, uint32_t world, const voi
 #define BL_LAUNCH(IDS, SM)                                                                              \
 	do {                                                                                                 \
 		static const int nb = per_sm(k_runs_lookup<IDS, SM>);                                            \
-		const uint64_t cap = (uint64_t)sm_count_() * nb;                                                 \
+		const uint64_t cap = (uint64_t)sm_count_() * limit_per_sm(nb);                                   \
 		k_runs_lookup<IDS, SM><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(idx->v, A, cnt, d_ctr); \
 	} while (0)
 	if (ret || out_ids) { if (idx->v.small) BL_LAUNCH(true, true); else BL_LAUNCH(true, false); }

@@ -10,11 +10,15 @@
 //   k_wait_counts      (owner, before its lookup kernel)    spins until every source's sequence number has arrived and
 //                      copies the counts next to the lookup kernel's arguments
 //
-// Stream order on every rank, sub-batch i using inbox half i & 1:   D(i)  P(i)  W(i)  L(i)
-//   (BLIGHT_PART_ORDER=ahead:  D(i+1)  L(i)  P(i+1)  W(i+1), so that the wait never sees the dispatch skew)
+// Order on every rank, sub-batch i using inbox half i & 1 (blight_part_config.order):
+//   serial    D(i)  P(i)  W(i)  L(i)                          one stream
+//   ahead     D(i+1)  L(i)  P(i+1)  W(i+1)                    one stream: the wait never sees the dispatch skew
+//   overlap   D(i+1) on the caller's stream BESIDE L(i) on a second one, each limited to half of every SM's CTA slots (the
+//             front end is arithmetic, the lookups are memory latency: together they fill the SM as the one-GPU kernel does);
+//             then P(i+1)  W(i+1)
 // A source rewrites half b in D(i+2), which follows its own W(i+1); W(i+1) needs every rank's P(i+1), which that rank
 // issued after its L(i): nobody is still reading the half. No deadlock: every wait depends only on kernels that precede
-// the matching publish in the publisher's own stream.
+// the matching publish in the publisher's own streams.
 // The ranks are processes (torchrun: buffers exchanged as CUDA IPC handles) or devices of one process
 // (blight_comm, comm.cu: peer access).
 #include <cuda_runtime.h>
@@ -100,7 +104,9 @@ struct blight_part_session {
 	unsigned long long* rcv[2] = {nullptr, nullptr};     // as an owner: counters received per source
 	uint32_t* err = nullptr;
 	unsigned long long seq = 0;  // sub-batches issued so far (same on every rank: the calls are collective)
-	bool ahead = false;
+	uint32_t order = BLIGHT_PART_ORDER_SERIAL;
+	cudaStream_t side = nullptr;  // overlap order: the lookups' stream
+	cudaEvent_t ev_main = nullptr, ev_side = nullptr;
 };
 
 extern "C" {
@@ -118,7 +124,12 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	blight_part_session* s = new blight_part_session();
 	s->idx = idx; s->device = idx->device; s->cfg = *cfg;
 	s->region_bytes = cfg->cap * BLIGHT_RUN_RECORD_BYTES;
-	if (const char* e = getenv("BLIGHT_PART_ORDER")) s->ahead = e[0] == 'a';
+	s->order = cfg->order;
+	if (s->order == BLIGHT_PART_ORDER_DEFAULT) {
+		s->order = BLIGHT_PART_ORDER_SERIAL;
+		if (const char* e = getenv("BLIGHT_PART_ORDER")) s->order = e[0] == 'a' ? BLIGHT_PART_ORDER_AHEAD : (e[0] == 'o' ? BLIGHT_PART_ORDER_OVERLAP : BLIGHT_PART_ORDER_SERIAL);
+	}
+	if (s->order > BLIGHT_PART_ORDER_OVERLAP) { delete s; return fail(BL_ERR_INVALID_ARG, "unknown order"); }
 	const size_t inbox_bytes = (size_t)2 * cfg->world * s->region_bytes;
 	cudaError_t e = cudaMalloc(&s->inbox, inbox_bytes);
 	if (e == cudaSuccess) e = cudaMemset(s->inbox, 0, inbox_bytes);  // a slot never written must still parse as a (harmless) record
@@ -132,6 +143,9 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	}
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->err), 4);
 	if (e == cudaSuccess) e = cudaMemset(s->err, 0, 4);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming);
 	if (e != cudaSuccess) { blight_part_session_free(s); return cu_fail(e, "partition session buffers"); }
 	// a rank is its own peer
 	const uint32_t r = cfg->rank;
@@ -154,6 +168,9 @@ void blight_part_session_free(blight_part_session* s) {
 	cudaFree(s->inbox); cudaFree(s->mail); cudaFree(s->ids);
 	for (int b = 0; b < 2; b++) { cudaFree(s->counts[b]); cudaFree(s->rcv[b]); }
 	cudaFree(s->err);
+	if (s->side) cudaStreamDestroy(s->side);
+	if (s->ev_main) cudaEventDestroy(s->ev_main);
+	if (s->ev_side) cudaEventDestroy(s->ev_side);
 	delete s;
 }
 
@@ -283,21 +300,39 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 		CU(cudaGetLastError());
 		return BL_OK;
 	};
-	auto lookup = [&](uint64_t i) -> int {
+	auto lookup_on = [&](uint64_t i, cudaStream_t on) -> int {
 		const int b = (int)(i & 1);
 		return blight_part_lookup_direct(s->idx, world, regions[b], reinterpret_cast<const uint64_t*>(s->rcv[b]), nullptr,
-		                                 want_ids ? out_ids : nullptr, want_ids ? s->p_ids_cap : nullptr, c.cap, c.sub_positions, d_ctr, st);
+		                                 want_ids ? out_ids : nullptr, want_ids ? s->p_ids_cap : nullptr, c.cap, c.sub_positions, d_ctr, on);
 	};
+	auto lookup = [&](uint64_t i) -> int { return lookup_on(i, st); };
 	int rc = BL_OK;
+	struct GridLimit { ~GridLimit() { g_part_blocks_per_sm = 0; } } grid_limit;  // whatever path leaves this function
 #define STEP(x) do { rc = (x); if (rc != BL_OK) return rc; } while (0)
-	if (!s->ahead) {
+	if (s->order == BLIGHT_PART_ORDER_SERIAL) {
 		for (uint64_t i = 0; i < n_sub; i++) { STEP(dispatch(i)); STEP(publish(i)); STEP(wait(i)); STEP(lookup(i)); }
-	} else if (n_sub) {
+	} else if (s->order == BLIGHT_PART_ORDER_AHEAD && n_sub) {
 		STEP(dispatch(0)); STEP(publish(0)); STEP(wait(0));
 		for (uint64_t i = 0; i < n_sub; i++) {
 			if (i + 1 < n_sub) STEP(dispatch(i + 1));
 			STEP(lookup(i));
 			if (i + 1 < n_sub) { STEP(publish(i + 1)); STEP(wait(i + 1)); }
+		}
+	} else if (n_sub) {
+		// overlap: the caller's stream carries D / P / W, the session's second stream the lookups; while both kinds of kernel
+		// are in flight each takes half of an SM's CTA slots, the first dispatch and the last lookup take all of them
+		STEP(dispatch(0)); STEP(publish(0)); STEP(wait(0));
+		for (uint64_t i = 0; i < n_sub; i++) {
+			const bool both = i + 1 < n_sub;
+			CU(cudaEventRecord(s->ev_main, st));              // W(i) done (and, for i = 0, whatever the caller queued before)
+			CU(cudaStreamWaitEvent(s->side, s->ev_main, 0));
+			g_part_blocks_per_sm = both ? 2 : 0;
+			STEP(lookup_on(i, s->side));
+			CU(cudaEventRecord(s->ev_side, s->side));
+			if (both) STEP(dispatch(i + 1));
+			g_part_blocks_per_sm = 0;
+			CU(cudaStreamWaitEvent(st, s->ev_side, 0));       // P(i+1) tells the peers this rank is done READING half i & 1 too
+			if (both) { STEP(publish(i + 1)); STEP(wait(i + 1)); }
 		}
 	}
 #undef STEP

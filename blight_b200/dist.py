@@ -34,6 +34,9 @@ import torch.distributed as dist
 from . import api
 
 
+DEFAULT_ORDER = "serial"  # kernel order of the fused partitioned path when neither the caller nor BLIGHT_PART_ORDER says (part_session.cu)
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous chunk [lo, hi) of n items for `rank` (sizes differ by at most one)."""
     base, rem = divmod(n, world)
@@ -229,7 +232,7 @@ class PartitionedSet:
         del self._inbox, self._ret, self._side
 
     def enable_fused(self, want_ids: bool = True, sub_positions: int = 64 << 20, records_per_position: Optional[float] = None,
-                     ids_capacity: int = 0, mode: Optional[str] = None):
+                     ids_capacity: int = 0, mode: Optional[str] = None, order: Optional[str] = None):
         """Allocates and exchanges the peer buffers. mode "session" (default): csrc/part_session.cu — per rank a double
         buffered inbox of world regions of `cap` records (written by the sources), a mailbox of flags, and for the id mode
         an id array of `ids_capacity` int64 (written by the owners; grown on demand by query_reads_fused). mode "stream":
@@ -249,6 +252,7 @@ class PartitionedSet:
             self._cap = min(max(1024, int(self._sub * records_per_position)), max_cap)
             self._world, self._rank, self._fused_ids = world, rank, want_ids
             self._session_args = (world, rank)
+            self._order = order or os.environ.get("BLIGHT_PART_ORDER") or DEFAULT_ORDER  # "serial" | "ahead" | "overlap"
             self._make_session(int(ids_capacity) if want_ids else 0)
             return
         if records_per_position is None:
@@ -326,7 +330,8 @@ class PartitionedSet:
                 dist.barrier(group=self.group)
             self._session.close()
         dev = torch.device("cuda", self.index.device)
-        self._session = api.PartSession(self.index, world, rank, self.plan.lb, self.plan.cuts, self._sub, self._cap, ids_capacity)
+        self._session = api.PartSession(self.index, world, rank, self.plan.lb, self.plan.cuts, self._sub, self._cap, ids_capacity,
+                                        order=self._order)
         everyone = [None] * world
         mine = (self._session.handles(), ids_capacity)
         if world > 1:

@@ -244,12 +244,16 @@ typedef struct blight_part_session blight_part_session;
 typedef struct blight_part_config {
 	uint32_t world, rank;
 	uint32_t lb;                         /* log2(buckets per MPHF group) */
-	uint32_t reserved;
+	uint32_t order;                      /* BLIGHT_PART_ORDER_*: how the kernels of consecutive sub-batches are ordered */
 	uint32_t cuts[BLIGHT_MAX_RANKS + 1]; /* rank r owns MPHF groups [cuts[r], cuts[r+1]) */
 	uint64_t sub_positions;              /* base positions per sub-batch (multiple of 256, < 2^32) */
 	uint64_t cap;                        /* records per (source, owner) inbox region and sub-batch (< 2^24) */
 	uint64_t ids_capacity;               /* entries of this rank's id array (0: counting mode only) */
 } blight_part_config;
+#define BLIGHT_PART_ORDER_DEFAULT 0u /* what BLIGHT_PART_ORDER says (serial | ahead | overlap), else the library's choice */
+#define BLIGHT_PART_ORDER_SERIAL 1u  /* dispatch(i), lookup(i), dispatch(i+1), ... on one stream */
+#define BLIGHT_PART_ORDER_AHEAD 2u   /* dispatch(i+1) before lookup(i) on one stream: the wait for the peers never sees dispatch skew */
+#define BLIGHT_PART_ORDER_OVERLAP 3u /* dispatch(i+1) BESIDE lookup(i) on two streams, each on half of every SM's CTA slots */
 #define BLIGHT_PART_OVERFLOW 1u /* status flag: an inbox region was too small, records were dropped (answer the batch another way) */
 #define BLIGHT_PART_TIMEOUT 2u  /* status flag: a peer's flag never arrived */
 int blight_part_session_create(const blight_index* local_slice, const blight_part_config* cfg, blight_part_session** out);

@@ -16,7 +16,7 @@ REF_SO = os.path.join(_HERE, "_ref", "libblight_ref.so")
 def build_cport(force: bool = False) -> str:
     src = os.path.join(_HERE, "blight_oracle.c")
     if force or not os.path.exists(CPORT_SO) or os.path.getmtime(CPORT_SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-march=x86-64-v3", "-o", CPORT_SO, src])
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fopenmp", "-march=x86-64-v3", "-o", CPORT_SO, src])
     return CPORT_SO
 
 
@@ -54,6 +54,7 @@ class CPort:
         L.blo_query_get_hash.argtypes = [vp, u64, C.c_uint32]; L.blo_query_get_hash.restype = C.c_int64
         L.blo_query_sequence_hash.argtypes = [vp, vp, u64, vp, vp, vp]; L.blo_query_sequence_hash.restype = C.c_int64
         L.blo_query_reads.argtypes = [vp, vp, vp, u64, vp, vp, vp]; L.blo_query_reads.restype = C.c_int
+        L.blo_query_reads_mt.argtypes = [vp, vp, vp, u64, vp, vp, vp, C.c_int]; L.blo_query_reads_mt.restype = C.c_int
         self.L = L
         self.h = L.blo_load(os.fsencode(blob_path))
         if not self.h:
@@ -88,7 +89,7 @@ class CPort:
             return ids[:got], canon[:got], mini[:got]
         return ids[:got]
 
-    def query_reads(self, bases, read_off, want_ids: bool = True):
+    def query_reads(self, bases, read_off, want_ids: bool = True, threads: int = 1):
         bases = _u8(bases)
         read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
         lens = np.diff(read_off.astype(np.int64))
@@ -97,8 +98,8 @@ class CPort:
         np.cumsum(nk, out=koff[1:])
         ids = np.empty(int(koff[-1]), dtype=np.int64) if want_ids else None
         ctr = np.zeros(3, dtype=np.uint64)
-        rc = self.L.blo_query_reads(self.h, bases.ctypes.data, read_off.ctypes.data, len(lens),
-                                    ids.ctypes.data if want_ids else None, koff.ctypes.data, ctr.ctypes.data)
+        rc = self.L.blo_query_reads_mt(self.h, bases.ctypes.data, read_off.ctypes.data, len(lens),
+                                       ids.ctypes.data if want_ids else None, koff.ctypes.data, ctr.ctypes.data, int(threads))
         if rc != 0:
             raise ValueError("Invalid char in DNA")
         return ids, ctr

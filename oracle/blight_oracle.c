@@ -288,24 +288,41 @@ int64_t blo_query_sequence_hash(const blo_index* x, const char* q, uint64_t len,
 /* Body of file_query's loop over pre-split reads (blight.cpp:780-789): reads shorter than k are skipped.
  * ids_out (optional) receives read r's ids at kmer_offs[r]. ctr[0]=found ctr[1]=not found ctr[2]=queries.
  * Returns 0, or -1 on an invalid base. */
+int blo_query_reads_mt(const blo_index* x, const char* bases, const uint64_t* offs, uint64_t n_reads, int64_t* ids_out,
+                       const uint64_t* kmer_offs, uint64_t* ctr, int threads);
+
 int blo_query_reads(const blo_index* x, const char* bases, const uint64_t* offs, uint64_t n_reads, int64_t* ids_out,
                     const uint64_t* kmer_offs, uint64_t* ctr) {
+	return blo_query_reads_mt(x, bases, offs, n_reads, ids_out, kmer_offs, ctr, 1);
+}
+
+/* The same over `threads` host threads (reads are independent, blight.cpp:776-790 does the same with OpenMP): lets the
+ * large-configuration parity tests check tens of millions of k-mers in seconds. */
+int blo_query_reads_mt(const blo_index* x, const char* bases, const uint64_t* offs, uint64_t n_reads, int64_t* ids_out,
+                       const uint64_t* kmer_offs, uint64_t* ctr, int threads) {
 	const unsigned k = x->h.k;
 	uint64_t maxlen = 0;
 	for (uint64_t r = 0; r < n_reads; r++) if (offs[r + 1] - offs[r] > maxlen) maxlen = offs[r + 1] - offs[r];
-	int64_t* tmp = (int64_t*)malloc(sizeof(int64_t) * (size_t)(maxlen + 1));
-	ctr[0] = ctr[1] = ctr[2] = 0;
-	for (uint64_t r = 0; r < n_reads; r++) {
-		const uint64_t len = offs[r + 1] - offs[r];
-		if (len < k) continue;
-		int64_t n = blo_query_sequence_hash(x, bases + offs[r], len, tmp, NULL, NULL);
-		if (n < 0) { free(tmp); return -1; }
-		for (int64_t i = 0; i < n; i++) {
-			if (tmp[i] >= 0) ctr[0]++; else ctr[1]++;
-			if (ids_out) ids_out[kmer_offs[r] + (uint64_t)i] = tmp[i];
+	uint64_t found = 0, notfound = 0, queries = 0;
+	int bad = 0;
+	if (threads < 1) threads = 1;
+	#pragma omp parallel num_threads(threads) reduction(+ : found, notfound, queries, bad)
+	{
+		int64_t* tmp = (int64_t*)malloc(sizeof(int64_t) * (size_t)(maxlen + 1));
+		#pragma omp for schedule(dynamic, 256)
+		for (int64_t r = 0; r < (int64_t)n_reads; r++) {
+			const uint64_t len = offs[r + 1] - offs[r];
+			if (len < k) continue;
+			int64_t n = blo_query_sequence_hash(x, bases + offs[r], len, tmp, NULL, NULL);
+			if (n < 0) { bad++; continue; }
+			for (int64_t i = 0; i < n; i++) {
+				if (tmp[i] >= 0) found++; else notfound++;
+				if (ids_out) ids_out[kmer_offs[r] + (uint64_t)i] = tmp[i];
+			}
+			queries += (uint64_t)n;
 		}
-		ctr[2] += (uint64_t)n;
+		free(tmp);
 	}
-	free(tmp);
-	return 0;
+	ctr[0] = found; ctr[1] = notfound; ctr[2] = queries;
+	return bad ? -1 : 0;
 }

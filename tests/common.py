@@ -117,3 +117,18 @@ def bucket_end_case(shape, workdir: str):
     lost = sorted(set(x[ids >= 0].tolist()) - set(x[own_found].tolist()))
     first = {int(v): int(ids[np.nonzero(x == np.uint64(v))[0][0]]) for v in lost}
     return flat, text, port, [(v, first[v]) for v in lost]
+
+
+def read_blob_fallback(path: str):
+    """(fallback keys, fallback ranks, per-group (fb_off, fb_count, id_offset)) of a BLFLAT01 blob: the keys no BBHash level
+    accommodated (bbhash.h:567-575)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    u64 = raw[40:40 + 88].view(np.uint64)
+    nb, nm = int(u64[0]), int(u64[1])
+    seq_words, pos_words, bits_words, ranks_total, fb_total = (int(u64[i]) for i in (6, 7, 8, 9, 10))
+    off = 128 + 8 * nb + (4 * nb + 7) // 8 * 8
+    recs = raw[off:off + nm * 208].view(np.uint64).reshape(nm, 26)
+    off += nm * 208 + 8 * (seq_words + pos_words + bits_words + ranks_total)
+    keys = raw[off:off + 8 * fb_total].view(np.uint64).copy()
+    vals = raw[off + 8 * fb_total:off + 16 * fb_total].view(np.uint64).copy()
+    return keys, vals, [(int(r[7]), int(r[8]), int(r[0])) for r in recs]

@@ -18,15 +18,15 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("ret", ["session", "session+ahead", "stream"])
+@pytest.mark.parametrize("ret", ["session", "session+ahead", "session+overlap", "stream"])
 def test_partition_ids_equal_replica_on_real_peers(ret):
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     env = dict(os.environ, BLIGHT_CHECK_GENOME="20000000", BLIGHT_CHECK_READS="400000", BLIGHT_CHECK_SUB=str(8 << 20), BLIGHT_CHECK_REPS="2",
                BLIGHT_PART_RETURN=ret.split("+")[0])
-    if ret.endswith("ahead"):
-        env["BLIGHT_PART_ORDER"] = "ahead"
+    if "+" in ret:
+        env["BLIGHT_PART_ORDER"] = ret.split("+")[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tools", "multigpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)

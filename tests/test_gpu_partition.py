@@ -53,11 +53,16 @@ def test_loopback_partition_matches_oracle(shape, mode, tmp_path, torch_cuda, mo
     torch.cuda.synchronize()
     assert torch.equal(ctr2.cpu(), ctr.cpu())
     # the experimental kernel order (dispatch of the next sub-batch ahead of the lookup of this one): same answers
-    monkeypatch.setenv("BLIGHT_PART_ORDER", "ahead")
-    ps.enable_fused(sub_positions=1 << 17)  # the order is read when the buffers are set up
-    ids3, ctr3 = ps.query_reads_fused(d_b, d_o, d_k, total)
-    torch.cuda.synchronize()
-    assert np.array_equal(ids3.cpu().numpy(), want) and torch.equal(ctr3.cpu(), ctr.cpu())
+    # the other kernel orders (dispatch of the next sub-batch ahead of / beside the lookup of this one): same answers
+    for order in ("ahead", "overlap"):
+        monkeypatch.setenv("BLIGHT_PART_ORDER", order)
+        ps.enable_fused(sub_positions=1 << 17, order=order)  # the order is fixed when the buffers are set up
+        ids3, ctr3 = ps.query_reads_fused(d_b, d_o, d_k, total)
+        torch.cuda.synchronize()
+        assert np.array_equal(ids3.cpu().numpy(), want) and torch.equal(ctr3.cpu(), ctr.cpu()), order
+        _, ctr4 = ps.query_reads_fused(d_b, d_o, want_ids=False)
+        torch.cuda.synchronize()
+        assert torch.equal(ctr4.cpu(), ctr.cpu()), order
 
 
 def test_loopback_ragged_and_tiny_reads(tmp_path, torch_cuda):
@@ -152,7 +157,7 @@ def test_three_owners_two_sources_on_one_gpu(tmp_path, torch_cuda):
     assert (int(ctr[0]), int(ctr[1]), int(ctr[2])) == (int(wctr[0]), int(wctr[1]), int(wctr[2]))
 
 
-def test_three_sessions_on_one_gpu(tmp_path, torch_cuda, monkeypatch):
+def test_three_sessions_on_one_gpu(tmp_path, torch_cuda):
     """Three ranks of the partitioned path as three sessions of ONE process on GPU 0 (connect_local, one stream each): the
     ordering between ranks is nothing but the device-side flags, exactly as between the GPUs of a box. Ranks hold unequal
     shares of the reads (one holds none); ids land in each rank's own id array; both kernel orders."""
@@ -166,8 +171,7 @@ def test_three_sessions_on_one_gpu(tmp_path, torch_cuda, monkeypatch):
     owners = [flat.slice(*plan.group_range(r)).upload(0) for r in range(world)]
     koff_all = synth.kmer_offsets(ro, 31)
     cutsr = [0, 6000, 9000, 9000]  # reads per rank: 6000, 3000, 0
-    for order in ("", "ahead"):
-        monkeypatch.setenv("BLIGHT_PART_ORDER", order)
+    for order in ("serial", "ahead", "overlap"):
         sub = 1 << 17
         sess, batches = [], []
         for r in range(world):
@@ -176,7 +180,7 @@ def test_three_sessions_on_one_gpu(tmp_path, torch_cuda, monkeypatch):
             po = (ro[lo:hi + 1] - ro[lo]) if hi > lo else np.zeros(1, dtype=np.uint64)
             d_b, d_o, d_k, total = _dev_batch(torch, pb, po)
             batches.append((d_b, d_o, d_k, total, want[int(koff_all[lo]):int(koff_all[hi])]))
-            sess.append(api.PartSession(owners[r], world, r, plan.lb, plan.cuts, sub, 1 << 15, max(total, 1)))
+            sess.append(api.PartSession(owners[r], world, r, plan.lb, plan.cuts, sub, 1 << 15, max(total, 1), order=order))
         for r in range(world):
             for q in range(world):
                 if q != r:
