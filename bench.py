@@ -398,8 +398,8 @@ def partition_leg(args, rank, world, local, dev):
 
     del scratch
     variants, same_all, ctr_ok_all, ovf_all = {}, True, True, False
-    for order in ("serial", "ahead", "overlap"):
-        part.enable_fused(sub_positions=args.partition_sub, ids_capacity=total, order=order)
+    for name, order, ret in (("serial", "serial", "stream"), ("ahead", "ahead", "stream"), ("overlap", "overlap", "stream"), ("serial/direct", "serial", "direct")):
+        part.enable_fused(sub_positions=args.partition_sub, ids_capacity=total, order=order, return_path=ret)
         ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
         torch.cuda.synchronize()
         same = torch.tensor([1 if torch.equal(ids_f, ids_one) else 0], device=dev)
@@ -411,7 +411,7 @@ def partition_leg(args, rank, world, local, dev):
         f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False))
         ovf = torch.tensor([1 if part.overflowed() else 0], device=dev)
         dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
-        variants[order] = {"ids_ms": f_ids_ms, "counting_ms": f_cnt_ms, "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms,
+        variants[name] = {"ids_ms": f_ids_ms, "counting_ms": f_cnt_ms, "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms,
                            "counting_vs_one_gpu": world * one_cnt_ms / f_cnt_ms, "ids_equal_replica": bool(same.item()),
                            "counters_equal_replica": ctr_ok, "overflow": bool(ovf.item())}
         same_all &= bool(same.item()); ctr_ok_all &= ctr_ok; ovf_all |= bool(ovf.item())
@@ -436,7 +436,7 @@ def partition_leg(args, rank, world, local, dev):
         "ids_equal_replica": same_all, "counters_equal_replica": ctr_ok_all, "overflow": ovf_all,
         "kernel_order": default_order, "by_kernel_order": variants,
         "device_bytes_per_gpu": local_bytes, "cuts": part.plan.cuts, "sub_positions": part._sub,
-        "return_path": "ids stored by the owner straight into the source's int64 id array; ordering between GPUs by device-side flags (csrc/part_session.cu)",
+        "return_path": "stream: an owner's warp stores its 32-bit ids as one contiguous run into the source's return region, the source widens them into read order one sub-batch behind; ordering between GPUs by device-side flags (csrc/part_session.cu)",
         "build_seconds": build_s, "leg_seconds": time.time() - t_leg,
     }
 
@@ -553,12 +553,14 @@ def main():
             idx.query_reads_host(hb, hr, want_ids=False)  # warm-up (sizes the library's device workspace and staging)
         sync_all()
         x0 = api.transfer_bytes()
+        k0 = api.host_pack_stats()
         t0 = time.perf_counter()
         for _ in range(e_steps):
             _, ectr = idx.query_reads_host(hb, hr, want_ids=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         x1 = api.transfer_bytes()
+        k1 = api.host_pack_stats()
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -568,6 +570,8 @@ def main():
                "ascii_bytes_per_step": int(h_bases.numel()), "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps,
                "mode": "bool (file_query counters), pinned host reads; part of the batch crosses PCIe 2-bit packed by the host cores (bytes as counted by the library)",
                "host_threads_near_gpu": len(cpus) if cpus else None,
+               "host_packer": {"threads": k1[2], "bases_packed_per_step": (k1[0] - k0[0]) // e_steps,
+                               "GB_per_s_while_packing": (k1[0] - k0[0]) / max(1e-9, k1[1] - k0[1]) / 1e9},
                "found": int(ectr[api.CTR_FOUND]), "not_found": int(ectr[api.CTR_NOT_FOUND])}
 
     # ---- file_query(path): 2-line FASTA file on tmpfs through kmer_Set_Light::file_query's replacement (N = 1) ----

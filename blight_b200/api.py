@@ -21,11 +21,11 @@ CTR_FOUND, CTR_NOT_FOUND, CTR_QUERIES, CTR_INVALID, N_CTR = 0, 1, 2, 3, 4
 
 # every symbol include/blight_b200.h declares
 SYMBOLS = [
-    "blight_version", "blight_last_error", "blight_check_params", "blight_flat_build_file", "blight_flat_build_seqs", "blight_flat_build_spans",
+    "blight_version", "blight_last_error", "blight_check_params", "blight_flat_build_file", "blight_flat_build_seqs", "blight_flat_build_spans", "blight_flat_build_gpu", "blight_flat_build_file_gpu",
     "blight_flat_save", "blight_flat_load", "blight_flat_free", "blight_flat_info", "blight_flat_compare",
     "blight_flat_slice", "blight_flat_group_sizes", "blight_index_upload", "blight_index_upload_opts", "blight_index_free", "blight_index_info",
     "blight_query_kmers", "blight_query_kmers_mini", "blight_reads_to_kmers", "blight_query_reads", "blight_query_reads_packed",
-    "blight_query_sequence_bool_host", "blight_transfer_bytes",
+    "blight_query_sequence_bool_host", "blight_transfer_bytes", "blight_host_pack_stats",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
     "blight_consume_reads", "blight_gather_reads", "blight_fasta_cut_stream", "blight_part_dispatch", "blight_part_lookup", "blight_part_lookup_direct", "blight_part_scatter",
@@ -49,10 +49,11 @@ class PartConfig(C.Structure):
     """blight_part_config (include/blight_b200.h)"""
     _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("lb", C.c_uint32), ("order", C.c_uint32),
                 ("cuts", C.c_uint32 * (MAX_RANKS + 1)), ("sub_positions", C.c_uint64), ("cap", C.c_uint64),
-                ("ids_capacity", C.c_uint64)]
+                ("ids_capacity", C.c_uint64), ("return_path", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 PART_OVERFLOW, PART_TIMEOUT = 1, 2
+PART_RETURNS = {None: 0, "": 0, "default": 0, "session": 0, "stream": 1, "direct": 2}
 PART_ORDERS = {None: 0, "": 0, "default": 0, "serial": 1, "ahead": 2, "overlap": 3}
 
 
@@ -118,6 +119,8 @@ def lib() -> C.CDLL:
     L.blight_flat_build_file.argtypes = [cp] + [u32] * 6 + [C.POINTER(vp)]
     L.blight_flat_build_seqs.argtypes = [vp, vp, u64] + [u32] * 6 + [C.POINTER(vp)]
     L.blight_flat_build_spans.argtypes = [vp, vp, vp, u64] + [u32] * 6 + [C.POINTER(vp)]
+    L.blight_flat_build_gpu.argtypes = [vp, vp, vp, u64] + [u32] * 5 + [C.c_int, C.POINTER(vp), C.POINTER(C.c_double)]
+    L.blight_flat_build_file_gpu.argtypes = [cp] + [u32] * 5 + [C.c_int, C.POINTER(vp)]
     L.blight_flat_save.argtypes = [vp, cp]
     L.blight_flat_load.argtypes = [cp, C.POINTER(vp)]
     L.blight_flat_free.argtypes = [vp]
@@ -139,6 +142,8 @@ def lib() -> C.CDLL:
     L.blight_query_sequence_bool_host.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.blight_transfer_bytes.argtypes = [C.POINTER(u64), C.POINTER(u64)]
     L.blight_transfer_bytes.restype = None
+    L.blight_host_pack_stats.argtypes = [C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)]
+    L.blight_host_pack_stats.restype = None
     L.blight_query_fasta_host.argtypes = [vp, vp, u64, vp]
     L.blight_query_file_host.argtypes = [vp, cp, vp]
     L.blight_query_sequence_host.argtypes = [vp, vp, u64, vp, C.POINTER(u64)]
@@ -159,7 +164,7 @@ def lib() -> C.CDLL:
     L.blight_part_session_free.argtypes = [vp]
     L.blight_part_session_free.restype = None
     L.blight_part_session_handles.argtypes = [vp, C.c_char_p]
-    L.blight_part_session_connect_ipc.argtypes = [vp, u32, C.c_char_p, u64]
+    L.blight_part_session_connect_ipc.argtypes = [vp, u32, C.c_char_p, u64, u64]
     L.blight_part_session_connect_local.argtypes = [vp, u32, vp]
     L.blight_part_session_ids.argtypes = [vp]
     L.blight_part_session_ids.restype = vp
@@ -201,6 +206,13 @@ def transfer_bytes():
     return int(a.value), int(b.value)
 
 
+def host_pack_stats():
+    """(bases packed to 2 bits by the host packer, seconds it spent packing, threads it uses) since load."""
+    a, b, t = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    lib().blight_host_pack_stats(C.byref(a), C.byref(b), C.byref(t))
+    return int(a.value), b.value * 1e-9, int(t.value)
+
+
 class FlatIndex:
     """Host-side flat index image (BLFLAT01)."""
 
@@ -231,6 +243,27 @@ class FlatIndex:
         h = C.c_void_p()
         _check(lib().blight_flat_build_spans(bases.ctypes.data, starts.ctypes.data, lengths.ctypes.data, len(starts),
                                              k, m, n, s, b, threads, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build_gpu(cls, bases: np.ndarray, starts: np.ndarray, lengths: np.ndarray, k=31, m=9, n=17, s=6, b=6, device=0) -> "FlatIndex":
+        """construct_index on the GPU (csrc/gpu_builder.cu): same flat image as the host builders, word for word.
+        The time between the first H2D copy and the last kernel is left in .gpu_build_seconds."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+        h = C.c_void_p()
+        sec = C.c_double()
+        _check(lib().blight_flat_build_gpu(bases.ctypes.data, starts.ctypes.data, lengths.ctypes.data, len(starts), k, m, n, s, b, device,
+                                           C.byref(h), C.byref(sec)))
+        out = cls(h.value)
+        out.gpu_build_seconds = float(sec.value)
+        return out
+
+    @classmethod
+    def build_file_gpu(cls, path: str, k=31, m=9, n=17, s=6, b=6, device=0) -> "FlatIndex":
+        h = C.c_void_p()
+        _check(lib().blight_flat_build_file_gpu(os.fsencode(path), k, m, n, s, b, device, C.byref(h)))
         return cls(h.value)
 
     @classmethod
@@ -550,8 +583,9 @@ class PartSession:
     id array, the peers' buffers, and the per-batch pipeline ordered by device-side flags."""
 
     def __init__(self, index: "DeviceIndex", world: int, rank: int, lb: int, cuts: Sequence[int], sub_positions: int, cap: int,
-                 ids_capacity: int = 0, order: Optional[str] = None):
+                 ids_capacity: int = 0, order: Optional[str] = None, return_path: Optional[str] = None):
         cfg = PartConfig()
+        cfg.return_path = PART_RETURNS[return_path]
         cfg.world, cfg.rank, cfg.lb, cfg.sub_positions, cfg.cap, cfg.ids_capacity = world, rank, lb, sub_positions, cap, ids_capacity
         cfg.order = PART_ORDERS[order]
         for i, c in enumerate(cuts):
@@ -562,12 +596,12 @@ class PartSession:
         self.sub_positions, self.cap, self.ids_capacity = sub_positions, cap, ids_capacity
 
     def handles(self) -> bytes:
-        buf = C.create_string_buffer(192)
+        buf = C.create_string_buffer(256)
         _check(lib().blight_part_session_handles(self._h, buf))
         return buf.raw
 
-    def connect_ipc(self, peer: int, handles: bytes, peer_ids_capacity: int):
-        _check(lib().blight_part_session_connect_ipc(self._h, peer, handles, peer_ids_capacity))
+    def connect_ipc(self, peer: int, handles: bytes, peer_ids_capacity: int, peer_id_base: int):
+        _check(lib().blight_part_session_connect_ipc(self._h, peer, handles, peer_ids_capacity, peer_id_base))
 
     def connect_local(self, peer: int, other: "PartSession"):
         _check(lib().blight_part_session_connect_local(self._h, peer, other._h))

@@ -1,6 +1,7 @@
 // capi_common.hpp — definitions shared by the two halves of the C ABI (capi_host.cpp, capi_device.cu).
 #pragma once
 #include <string>
+#include <vector>
 
 #include "errors.hpp"
 #include "flat_index.hpp"
@@ -14,6 +15,9 @@ int fail(int code, const std::string& msg);
 void fill_info(const FlatIndex& f, blight_info* out);
 // Keeps MPHF groups [g_begin, g_end): other buckets become empty, arrays are compacted, ids stay global.
 int flat_slice(const FlatIndex& f, uint64_t g_begin, uint64_t g_end, FlatIndex& out, std::string* err);
+// gpu_builder.cu: construct_index on the GPU; sequences are views [starts[i], starts[i] + lens[i]) of text (host memory)
+int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<uint64_t>& starts, const std::vector<uint64_t>& lens,
+                         const BuildParams& P, int device, FlatIndex& out, std::string* err, double* seconds_device);
 // stream_query.cu: file_query(path) chunk by chunk (reader thread -> parallel record cut -> H2D / kernel overlap)
 int stream_file_query(const struct ::blight_index* idx, const char* path, uint64_t* ctr);
 void stream_ctx_free(void* ctx);

@@ -17,12 +17,14 @@
 // threads (the reference's callers query from OpenMP loops, Abundance_De_Bruijn_graph_snippet.cpp:122-125) each take their
 // own context instead of serialising on one stream.
 #include <cuda_runtime.h>
-#include <omp.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -35,7 +37,7 @@
 using namespace blight;
 
 namespace blight {
-std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
+std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0}, g_packed_bases{0}, g_pack_ns{0};
 }
 
 namespace {
@@ -53,7 +55,68 @@ struct DeviceGuard {
 	~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// The packer's own worker threads (not OpenMP: the process may hold a second OpenMP runtime — PyTorch ships one — and a
+// team forked from a short-lived thread is neither cheap nor reliably wide). Workers pull block numbers from a shared counter.
+class PackPool {
+public:
+	explicit PackPool(int n_threads) {
+		for (int i = 1; i < n_threads; i++) workers_.emplace_back([this] { loop(); });
+	}
+	~PackPool() {
+		{ std::lock_guard<std::mutex> l(m_); stop_ = true; gen_++; }
+		cv_.notify_all();
+		for (auto& t : workers_) t.join();
+	}
+	// packs text[0, n_bases) into words; false if a byte outside ACGTacgt was seen. The caller works too.
+	bool run(const char* text, uint64_t n_bases, uint32_t* words) {
+		text_ = text; n_bases_ = n_bases; words_ = words;
+		n_blocks_ = int64_t((n_bases + kBlock - 1) / kBlock);
+		next_.store(0); bad_.store(0);
+		{ std::lock_guard<std::mutex> l(m_); pending_ = (int)workers_.size(); gen_++; }
+		cv_.notify_all();
+		work();
+		std::unique_lock<std::mutex> l(m_);
+		done_.wait(l, [&] { return pending_ == 0; });
+		return bad_.load() == 0;
+	}
+	int threads() const { return (int)workers_.size() + 1; }
+
+private:
+	static constexpr uint64_t kBlock = 1u << 16;  // bases per block: a multiple of 16, every block starts on a word
+	void work() {
+		for (;;) {
+			const int64_t b = next_.fetch_add(1);
+			if (b >= n_blocks_) return;
+			const uint64_t o = uint64_t(b) * kBlock;
+			if (!pack2_block(text_ + o, std::min<uint64_t>(kBlock, n_bases_ - o), words_ + (o >> 4))) bad_.fetch_add(1);
+		}
+	}
+	void loop() {
+		uint64_t seen = 0;
+		for (;;) {
+			{
+				std::unique_lock<std::mutex> l(m_);
+				cv_.wait(l, [&] { return gen_ != seen; });
+				seen = gen_;
+				if (stop_) return;
+			}
+			work();
+			{ std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_one(); }
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::mutex m_;
+	std::condition_variable cv_, done_;
+	uint64_t gen_ = 0;
+	int pending_ = 0;
+	bool stop_ = false;
+	const char* text_ = nullptr; uint64_t n_bases_ = 0; uint32_t* words_ = nullptr; int64_t n_blocks_ = 0;
+	std::atomic<int64_t> next_{0};
+	std::atomic<int> bad_{0};
+};
+
 struct HostCtx {
+	std::unique_ptr<PackPool> pool;
 	cudaStream_t st_f = nullptr, st_b = nullptr, cs_raw = nullptr, cs_pk = nullptr;
 	cudaEvent_t ev_f[2] = {nullptr, nullptr}, ev_slot[kSlots] = {nullptr, nullptr, nullptr}, ev_join = nullptr;
 	uint32_t* stage[kSlots] = {nullptr, nullptr, nullptr};
@@ -216,7 +279,7 @@ int front_producer(Plan& P) {
 	}
 }
 
-int back_producer(Plan& P, int threads) {
+int back_producer(Plan& P) {
 	HostCtx& C = *P.C;
 	for (int nb = 0;; nb++) {
 		const int c = P.claim_back();
@@ -225,15 +288,11 @@ int back_producer(Plan& P, int threads) {
 		if (nb >= kSlots) CU(cudaEventSynchronize(C.ev_slot[s]));  // the copy that last read this staging buffer has left
 		const uint64_t c0 = P.cut[c], upto = std::min(P.len, P.cut[c + 1] + kHalo);
 		const uint64_t n_bases = upto - c0, n_words = (n_bases + 15) / 16;
-		// pack in blocks of 64 K bases (a multiple of 16: every block starts on a word)
-		const int64_t n_blocks = int64_t((n_bases + 65535) >> 16);
-		int bad = 0;
-		#pragma omp parallel for num_threads(threads) schedule(static) reduction(+ : bad)
-		for (int64_t b = 0; b < n_blocks; b++) {
-			const uint64_t o = uint64_t(b) << 16;
-			if (!pack2_block(P.text + c0 + o, std::min<uint64_t>(65536, n_bases - o), C.stage[s] + (o >> 4))) bad++;
-		}
+		const auto t0 = std::chrono::steady_clock::now();
+		const bool bad = !C.pool->run(P.text + c0, n_bases, C.stage[s]);
+		g_pack_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
 		if (!bad) {
+			g_packed_bases += n_bases;
 			CU(cudaMemcpyAsync(P.d_packed + (c0 >> 4), C.stage[s], n_words * 4, cudaMemcpyHostToDevice, C.cs_pk));
 			g_h2d_bytes += n_words * 4;
 		} else {
@@ -289,6 +348,7 @@ int host_query_records(const blight_index* idx, const char* text, uint64_t len, 
 		if ((rc = C.reserve(6, (len + 15) / 16 * 4 + 256, &p)) != BL_OK) return rc;
 		P.d_packed = static_cast<uint32_t*>(p);
 		if ((rc = C.reserve_stage((chunk + kHalo + 15) / 16 * 4 + 64)) != BL_OK) return rc;
+		if (!C.pool || C.pool->threads() != threads) C.pool.reset(new PackPool(threads));
 	}
 	// chunks: the first ones small (4 MB, doubling), so the first kernel starts after 0.1 ms of copy instead of a millisecond
 	P.cut.push_back(0);
@@ -307,7 +367,7 @@ int host_query_records(const blight_index* idx, const char* text, uint64_t len, 
 	if (pack) {
 		back = std::thread([&] {
 			cudaSetDevice(idx->device);
-			rc_back = back_producer(P, threads);
+			rc_back = back_producer(P);
 			if (rc_back != BL_OK) err_back = g_last_error;
 		});
 	}
@@ -425,6 +485,12 @@ int blight_query_kmers_host(const blight_index* idx, const uint64_t* canon, uint
 void blight_transfer_bytes(uint64_t* h2d, uint64_t* d2h) {
 	if (h2d) *h2d = g_h2d_bytes.load();
 	if (d2h) *d2h = g_d2h_bytes.load();
+}
+
+void blight_host_pack_stats(uint64_t* packed_bases, uint64_t* pack_ns, uint32_t* threads) {
+	if (packed_bases) *packed_bases = g_packed_bases.load();
+	if (pack_ns) *pack_ns = g_pack_ns.load();
+	if (threads) *threads = (uint32_t)pack_threads();
 }
 
 }  // extern "C"

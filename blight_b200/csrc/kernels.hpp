@@ -64,6 +64,7 @@ int launch_reads_sink(const DevIndexView& I, int kind, const ReadBatch& B, uint3
 int part_dispatch_batch(uint32_t k, uint32_t m, const ReadBatch& B, uint64_t pos_begin, uint64_t pos_end, const ::blight_part_route* route,
                         uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream);
 
+int part_kernels_preload();
 // resident CTAs per SM the next dispatch / lookup launches of the calling thread may take (0: all that fit)
 extern thread_local int g_part_blocks_per_sm;
 // part_session.cu: blight_part_session_query on a ReadBatch (records with explicit ends, packed text)

@@ -570,6 +570,22 @@ int blight_part_dispatch(uint32_t k, uint32_t m, const char* d_bases, const uint
 }  // extern "C"
 
 namespace blight {
+// Loads every kernel of the partitioned path now. With lazy module loading the first launch of a kernel may have to wait
+// for the device to drain — which never happens while another rank's wait kernel spins on a flag this rank has yet to
+// publish. Sessions call this when they are created (nothing is in flight then).
+int part_kernels_preload() {
+	cudaFuncAttributes a;
+	cudaError_t e = cudaFuncGetAttributes(&a, k_dispatch_runs<true>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_dispatch_runs<false>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_runs_lookup<true, true>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_runs_lookup<true, false>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_runs_lookup<false, true>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_runs_lookup<false, false>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_scatter_runs);
+	(void)per_sm(k_dispatch_runs<true>); (void)per_sm(k_dispatch_runs<false>);
+	return e == cudaSuccess ? BL_OK : fail(BL_ERR_CUDA, std::string("cannot load the partition kernels: ") + cudaGetErrorString(e));
+}
+
 int part_dispatch_batch(uint32_t k, uint32_t m, const ReadBatch& B, uint64_t pos_begin, uint64_t pos_end, const blight_part_route* route,
                         uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream) {
 	const uint64_t n_reads = B.n_reads, total_bases = B.total_bases;

@@ -19,11 +19,20 @@
 // A source rewrites half b in D(i+2), which follows its own W(i+1); W(i+1) needs every rank's P(i+1), which that rank
 // issued after its L(i): nobody is still reading the half. No deadlock: every wait depends only on kernels that precede
 // the matching publish in the publisher's own streams.
+// Identifiers return one of two ways (blight_part_config.return_path):
+//   stream    (default) an owner's warp stores its answers as ONE contiguous run of 32-bit slice-local ids into its return
+//             region at the source; the source widens them into its int64 id array in read order through a local side table
+//             (k_scatter_runs), one sub-batch behind, on its own stream. S(i) may start once W(i+1) has passed: every owner
+//             published P(i+1) after its L(i).
+//   direct    the owner stores int64 ids straight into the source's id array, run by run. No second pass, but the stores are
+//             ~100-byte segments scattered over a multi-GB array: measured on 8 B200s 160 GB/s per GPU (38.8 ms per batch
+//             of 480 M k-mers) against 17.4 ms for counting — kept for two-GPU boxes, where it is free.
 // The ranks are processes (torchrun: buffers exchanged as CUDA IPC handles) or devices of one process
 // (blight_comm, comm.cu: peer access).
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -91,12 +100,16 @@ struct blight_part_session {
 	// this rank's peer-visible buffers
 	void* inbox = nullptr;     // [2][world sources][cap] records
 	Mailbox* mail = nullptr;
-	int64_t* ids = nullptr;    // id array the owners write into (direct return), ids_capacity entries
+	int64_t* ids = nullptr;    // this rank's id array, ids_capacity entries (direct return: the owners write into it)
+	uint32_t* ret = nullptr;   // stream return: [2][world owners][sub_positions] 32-bit ids, written by the owners
+	uint4* side = nullptr;     // stream return, local: [2][world owners][cap] where each record's ids go
 	// the other ranks' buffers as seen from here
 	void* p_inbox[kMaxRanks] = {};
 	Mailbox* p_mail[kMaxRanks] = {};
 	int64_t* p_ids[kMaxRanks] = {};
+	uint32_t* p_ret[kMaxRanks] = {};
 	uint64_t p_ids_cap[kMaxRanks] = {};
+	uint64_t id_base[kMaxRanks] = {};  // first identifier of every rank's slice
 	bool ipc_opened[kMaxRanks] = {};
 	uint32_t connected = 0;
 	// local scratch
@@ -105,8 +118,11 @@ struct blight_part_session {
 	uint32_t* err = nullptr;
 	unsigned long long seq = 0;  // sub-batches issued so far (same on every rank: the calls are collective)
 	uint32_t order = BLIGHT_PART_ORDER_SERIAL;
-	cudaStream_t side = nullptr;  // overlap order: the lookups' stream
-	cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+	bool stream_ret = true;
+	int split_lookup = 2, split_dispatch = 2;  // overlap order: resident CTAs per SM of either kernel while both run
+	cudaStream_t side_st = nullptr;  // overlap order: the lookups' stream
+	cudaStream_t scat_st = nullptr;  // stream return: the scatter pass
+	cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_pub = nullptr, ev_scat[2] = {nullptr, nullptr};
 };
 
 extern "C" {
@@ -121,6 +137,13 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 		if (cfg->cuts[i] > cfg->cuts[i + 1]) return fail(BL_ERR_INVALID_ARG, "cuts must ascend");
 	if (cfg->ids_capacity && !idx->v.pos_id) return fail(BL_ERR_INVALID_ARG, "the id mode of the partitioned path needs the position->id table");
 	Guard g(idx->device);
+	{
+		int rc = part_kernels_preload();
+		cudaFuncAttributes fa;
+		if (rc == BL_OK && (cudaFuncGetAttributes(&fa, k_publish_counts) != cudaSuccess || cudaFuncGetAttributes(&fa, k_wait_counts) != cudaSuccess))
+			rc = fail(BL_ERR_CUDA, "cannot load the flag kernels");
+		if (rc != BL_OK) return rc;
+	}
 	blight_part_session* s = new blight_part_session();
 	s->idx = idx; s->device = idx->device; s->cfg = *cfg;
 	s->region_bytes = cfg->cap * BLIGHT_RUN_RECORD_BYTES;
@@ -130,12 +153,27 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 		if (const char* e = getenv("BLIGHT_PART_ORDER")) s->order = e[0] == 'a' ? BLIGHT_PART_ORDER_AHEAD : (e[0] == 'o' ? BLIGHT_PART_ORDER_OVERLAP : BLIGHT_PART_ORDER_SERIAL);
 	}
 	if (s->order > BLIGHT_PART_ORDER_OVERLAP) { delete s; return fail(BL_ERR_INVALID_ARG, "unknown order"); }
+	if (const char* e = getenv("BLIGHT_PART_SPLIT")) {  // "L,D": CTAs per SM of the lookup and the dispatch kernel in the overlap order
+		int a = 0, bb = 0;
+		if (sscanf(e, "%d,%d", &a, &bb) == 2 && a > 0 && bb > 0) { s->split_lookup = a; s->split_dispatch = bb; }
+	}
+	uint32_t rp = cfg->return_path;
+	if (rp == BLIGHT_PART_RETURN_DEFAULT) {
+		rp = BLIGHT_PART_RETURN_STREAM;
+		if (const char* e = getenv("BLIGHT_PART_RETURN")) rp = e[0] == 'd' ? BLIGHT_PART_RETURN_DIRECT : BLIGHT_PART_RETURN_STREAM;
+	}
+	if (rp != BLIGHT_PART_RETURN_STREAM && rp != BLIGHT_PART_RETURN_DIRECT) { delete s; return fail(BL_ERR_INVALID_ARG, "unknown return path"); }
+	s->stream_ret = rp == BLIGHT_PART_RETURN_STREAM;
 	const size_t inbox_bytes = (size_t)2 * cfg->world * s->region_bytes;
 	cudaError_t e = cudaMalloc(&s->inbox, inbox_bytes);
 	if (e == cudaSuccess) e = cudaMemset(s->inbox, 0, inbox_bytes);  // a slot never written must still parse as a (harmless) record
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->mail), sizeof(Mailbox));
 	if (e == cudaSuccess) e = cudaMemset(s->mail, 0, sizeof(Mailbox));
 	if (e == cudaSuccess && cfg->ids_capacity) e = cudaMalloc(reinterpret_cast<void**>(&s->ids), (size_t)cfg->ids_capacity * 8);
+	if (e == cudaSuccess && cfg->ids_capacity && s->stream_ret) {
+		e = cudaMalloc(reinterpret_cast<void**>(&s->ret), (size_t)2 * cfg->world * cfg->sub_positions * 4);
+		if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->side), (size_t)2 * cfg->world * cfg->cap * sizeof(uint4));
+	}
 	for (int b = 0; b < 2 && e == cudaSuccess; b++) {
 		e = cudaMalloc(reinterpret_cast<void**>(&s->counts[b]), kMaxRanks * 8);
 		if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->rcv[b]), kMaxRanks * 8);
@@ -143,13 +181,14 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	}
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->err), 4);
 	if (e == cudaSuccess) e = cudaMemset(s->err, 0, 4);
-	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side_st, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming);
 	if (e != cudaSuccess) { blight_part_session_free(s); return cu_fail(e, "partition session buffers"); }
 	// a rank is its own peer
 	const uint32_t r = cfg->rank;
-	s->p_inbox[r] = s->inbox; s->p_mail[r] = s->mail; s->p_ids[r] = s->ids; s->p_ids_cap[r] = cfg->ids_capacity;
+	s->p_inbox[r] = s->inbox; s->p_mail[r] = s->mail; s->p_ids[r] = s->ids; s->p_ids_cap[r] = cfg->ids_capacity; s->p_ret[r] = s->ret;
+	s->id_base[r] = idx->info.id_base;
 	s->connected = 1u << r;
 	*out = s;
 	return BL_OK;
@@ -164,22 +203,24 @@ void blight_part_session_free(blight_part_session* s) {
 			cudaIpcCloseMemHandle(s->p_inbox[r]);
 			cudaIpcCloseMemHandle(s->p_mail[r]);
 			if (s->p_ids[r]) cudaIpcCloseMemHandle(s->p_ids[r]);
+			if (s->p_ret[r]) cudaIpcCloseMemHandle(s->p_ret[r]);
 		}
-	cudaFree(s->inbox); cudaFree(s->mail); cudaFree(s->ids);
+	cudaFree(s->inbox); cudaFree(s->mail); cudaFree(s->ids); cudaFree(s->ret); cudaFree(s->side);
 	for (int b = 0; b < 2; b++) { cudaFree(s->counts[b]); cudaFree(s->rcv[b]); }
 	cudaFree(s->err);
-	if (s->side) cudaStreamDestroy(s->side);
-	if (s->ev_main) cudaEventDestroy(s->ev_main);
-	if (s->ev_side) cudaEventDestroy(s->ev_side);
+	if (s->side_st) cudaStreamDestroy(s->side_st);
+	if (s->scat_st) cudaStreamDestroy(s->scat_st);
+	for (cudaEvent_t ev : {s->ev_main, s->ev_side, s->ev_pub, s->ev_scat[0], s->ev_scat[1]}) if (ev) cudaEventDestroy(ev);
 	delete s;
 }
 
-int blight_part_session_handles(const blight_part_session* s, unsigned char* handles192) {
-	if (!s || !handles192) return fail(BL_ERR_INVALID_ARG, "null argument");
+int blight_part_session_handles(const blight_part_session* s, unsigned char* handles256) {
+	unsigned char* handles192 = handles256;
+	if (!s || !handles256) return fail(BL_ERR_INVALID_ARG, "null argument");
 	Guard g(s->device);
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
 	cudaIpcMemHandle_t h;
-	std::memset(handles192, 0, 192);
+	std::memset(handles256, 0, 256);
 	CU(cudaIpcGetMemHandle(&h, s->inbox));
 	std::memcpy(handles192, &h, 64);
 	CU(cudaIpcGetMemHandle(&h, s->mail));
@@ -188,11 +229,17 @@ int blight_part_session_handles(const blight_part_session* s, unsigned char* han
 		CU(cudaIpcGetMemHandle(&h, s->ids));
 		std::memcpy(handles192 + 128, &h, 64);
 	}
+	if (s->ret) {
+		CU(cudaIpcGetMemHandle(&h, s->ret));
+		std::memcpy(handles256 + 192, &h, 64);
+	}
 	return BL_OK;
 }
 
-int blight_part_session_connect_ipc(blight_part_session* s, uint32_t peer, const unsigned char* handles192, uint64_t peer_ids_capacity) {
-	if (!s || !handles192) return fail(BL_ERR_INVALID_ARG, "null argument");
+int blight_part_session_connect_ipc(blight_part_session* s, uint32_t peer, const unsigned char* handles256, uint64_t peer_ids_capacity,
+                                    uint64_t peer_id_base) {
+	const unsigned char* handles192 = handles256;
+	if (!s || !handles256) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (peer >= s->cfg.world || peer == s->cfg.rank) return fail(BL_ERR_INVALID_ARG, "peer rank");
 	Guard g(s->device);
 	cudaIpcMemHandle_t h;
@@ -208,7 +255,13 @@ int blight_part_session_connect_ipc(blight_part_session* s, uint32_t peer, const
 		CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
 		s->p_ids[peer] = static_cast<int64_t*>(p);
 		s->p_ids_cap[peer] = peer_ids_capacity;
+		if (s->stream_ret) {
+			std::memcpy(&h, handles256 + 192, 64);
+			CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+			s->p_ret[peer] = static_cast<uint32_t*>(p);
+		}
 	}
+	s->id_base[peer] = peer_id_base;
 	s->ipc_opened[peer] = true;
 	s->connected |= 1u << peer;
 	return BL_OK;
@@ -230,6 +283,9 @@ int blight_part_session_connect_local(blight_part_session* s, uint32_t peer, con
 	s->p_mail[peer] = other->mail;
 	s->p_ids[peer] = other->ids;
 	s->p_ids_cap[peer] = other->cfg.ids_capacity;
+	s->p_ret[peer] = other->ret;
+	s->id_base[peer] = other->idx->info.id_base;
+	if (other->stream_ret != s->stream_ret) return fail(BL_ERR_INVALID_ARG, "the ranks disagree on the return path");
 	s->connected |= 1u << peer;
 	return BL_OK;
 }
@@ -261,24 +317,33 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 	const uint32_t world = c.world;
 	const long long spin_limit = 60ll * 2000000000ll;  // ~60 s of SM clock
 
+	const bool stream_ret = want_ids && s->stream_ret;
 	blight_part_route routes[2];
 	const void* regions[2][kMaxRanks];
+	void* ret_at[2][kMaxRanks];  // stream return: this owner's region at every source
 	for (int b = 0; b < 2; b++) {
 		blight_part_route& rt = routes[b];
 		std::memset(&rt, 0, sizeof rt);
-		rt.world = world; rt.rank = c.rank; rt.lb = c.lb; rt.cap = c.cap; rt.kcap = c.sub_positions; rt.side = nullptr;
+		rt.world = world; rt.rank = c.rank; rt.lb = c.lb; rt.cap = c.cap; rt.kcap = c.sub_positions;
+		rt.side = stream_ret ? static_cast<void*>(s->side + (size_t)b * world * c.cap) : nullptr;
 		for (uint32_t i = 0; i <= world; i++) rt.cuts[i] = c.cuts[i];
 		for (uint32_t d = 0; d < world; d++) {
 			rt.inbox[d] = static_cast<char*>(s->p_inbox[d]) + ((size_t)b * world + c.rank) * s->region_bytes;  // [half b][source = me] at owner d
 			regions[b][d] = static_cast<const char*>(s->inbox) + ((size_t)b * world + d) * s->region_bytes;   // [half b][source d] here
+			ret_at[b][d] = stream_ret ? static_cast<void*>(s->p_ret[d] + ((size_t)b * world + c.rank) * c.sub_positions) : nullptr;  // [half b][owner = me] at source d
 		}
 	}
 	MailPtrs mp{};
 	void* out_ids[kMaxRanks];
 	for (uint32_t d = 0; d < world; d++) { mp.m[d] = s->p_mail[d]; out_ids[d] = s->p_ids[d]; }
+	bool scat_pending[2] = {false, false};
 
 	auto dispatch = [&](uint64_t i) -> int {
 		const int b = (int)(i & 1);
+		if (scat_pending[b]) {  // the scatter of sub-batch i-2 still reads this half's counters, side table and return regions
+			CU(cudaStreamWaitEvent(st, s->ev_scat[b], 0));
+			scat_pending[b] = false;
+		}
 		CU(cudaMemsetAsync(s->counts[b], 0, kMaxRanks * 8, st));
 		const uint64_t lo = i * c.sub_positions;
 		if (lo < total_bases && n_reads) {
@@ -302,40 +367,62 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 	};
 	auto lookup_on = [&](uint64_t i, cudaStream_t on) -> int {
 		const int b = (int)(i & 1);
-		return blight_part_lookup_direct(s->idx, world, regions[b], reinterpret_cast<const uint64_t*>(s->rcv[b]), nullptr,
-		                                 want_ids ? out_ids : nullptr, want_ids ? s->p_ids_cap : nullptr, c.cap, c.sub_positions, d_ctr, on);
+		return blight_part_lookup_direct(s->idx, world, regions[b], reinterpret_cast<const uint64_t*>(s->rcv[b]), stream_ret ? ret_at[b] : nullptr,
+		                                 want_ids && !stream_ret ? out_ids : nullptr, want_ids && !stream_ret ? s->p_ids_cap : nullptr, c.cap,
+		                                 c.sub_positions, d_ctr, on);
 	};
 	auto lookup = [&](uint64_t i) -> int { return lookup_on(i, st); };
+	// stream return: sub-batch i's ids into the id array, on the scatter stream, once the main stream has passed a point
+	// after which every owner is known to have finished L(i) (the wait of sub-batch i+1, or the end-of-batch fence)
+	auto scatter = [&](uint64_t i) -> int {
+		if (!stream_ret) return BL_OK;
+		const int b = (int)(i & 1);
+		CU(cudaEventRecord(s->ev_pub, st));
+		CU(cudaStreamWaitEvent(s->scat_st, s->ev_pub, 0));
+		int rc = blight_part_scatter(s->side + (size_t)b * world * c.cap, c.cap, reinterpret_cast<const uint64_t*>(s->counts[b]),
+		                             s->ret + (size_t)b * world * c.sub_positions, c.sub_positions, world, (uint64_t)world * c.cap, s->id_base, s->ids,
+		                             s->scat_st);
+		if (rc != BL_OK) return rc;
+		CU(cudaEventRecord(s->ev_scat[b], s->scat_st));
+		scat_pending[b] = true;
+		return BL_OK;
+	};
 	int rc = BL_OK;
 	struct GridLimit { ~GridLimit() { g_part_blocks_per_sm = 0; } } grid_limit;  // whatever path leaves this function
 #define STEP(x) do { rc = (x); if (rc != BL_OK) return rc; } while (0)
 	if (s->order == BLIGHT_PART_ORDER_SERIAL) {
-		for (uint64_t i = 0; i < n_sub; i++) { STEP(dispatch(i)); STEP(publish(i)); STEP(wait(i)); STEP(lookup(i)); }
+		for (uint64_t i = 0; i < n_sub; i++) {
+			STEP(dispatch(i)); STEP(publish(i)); STEP(wait(i));
+			if (i) STEP(scatter(i - 1));
+			STEP(lookup(i));
+		}
 	} else if (s->order == BLIGHT_PART_ORDER_AHEAD && n_sub) {
 		STEP(dispatch(0)); STEP(publish(0)); STEP(wait(0));
 		for (uint64_t i = 0; i < n_sub; i++) {
+			if (i) STEP(scatter(i - 1));
 			if (i + 1 < n_sub) STEP(dispatch(i + 1));
 			STEP(lookup(i));
 			if (i + 1 < n_sub) { STEP(publish(i + 1)); STEP(wait(i + 1)); }
 		}
 	} else if (n_sub) {
 		// overlap: the caller's stream carries D / P / W, the session's second stream the lookups; while both kinds of kernel
-		// are in flight each takes half of an SM's CTA slots, the first dispatch and the last lookup take all of them
+		// are in flight each takes a share of an SM's CTA slots, the first dispatch and the last lookup take all of them
 		STEP(dispatch(0)); STEP(publish(0)); STEP(wait(0));
 		for (uint64_t i = 0; i < n_sub; i++) {
 			const bool both = i + 1 < n_sub;
+			if (i) STEP(scatter(i - 1));
 			CU(cudaEventRecord(s->ev_main, st));              // W(i) done (and, for i = 0, whatever the caller queued before)
-			CU(cudaStreamWaitEvent(s->side, s->ev_main, 0));
-			g_part_blocks_per_sm = both ? 2 : 0;
-			STEP(lookup_on(i, s->side));
-			CU(cudaEventRecord(s->ev_side, s->side));
+			CU(cudaStreamWaitEvent(s->side_st, s->ev_main, 0));
+			g_part_blocks_per_sm = both ? s->split_lookup : 0;
+			STEP(lookup_on(i, s->side_st));
+			CU(cudaEventRecord(s->ev_side, s->side_st));
+			g_part_blocks_per_sm = both ? s->split_dispatch : 0;
 			if (both) STEP(dispatch(i + 1));
 			g_part_blocks_per_sm = 0;
 			CU(cudaStreamWaitEvent(st, s->ev_side, 0));       // P(i+1) tells the peers this rank is done READING half i & 1 too
 			if (both) { STEP(publish(i + 1)); STEP(wait(i + 1)); }
 		}
 	}
-#undef STEP
 	// end-of-batch fence: once every rank's flag is here, every owner has finished its lookups, so the identifiers it stored
 	// into this rank's id array have landed
 	k_publish_counts<<<1, kMaxRanks, 0, st>>>(mp, nullptr, world, c.rank, 2u, s->seq + n_sub + 1);
@@ -343,6 +430,10 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 	g_launches += 2;
 	CU(cudaGetLastError());
 	s->seq += n_sub + 1;
+	if (n_sub) STEP(scatter(n_sub - 1));
+	for (int b = 0; b < 2; b++)
+		if (scat_pending[b]) CU(cudaStreamWaitEvent(st, s->ev_scat[b], 0));
+#undef STEP
 	return BL_OK;
 }
 

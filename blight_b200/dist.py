@@ -9,10 +9,11 @@ PartitionedSet   large indices: the 2^n MPHF groups are cut into `world` contigu
 
 PartitionedSet has two data paths. `query_reads_fused` is the product on NVLink boxes: the exchange is fused into the
 two kernels either side of it (csrc/part_kernels.cu) — the source stores one 32-byte record per super-k-mer straight into
-the owner's inbox (peer memory), the owner stores int64 ids straight into the source's id array; the ordering between GPUs
+the owner's inbox (peer memory), the owner stores its ids straight into the source's memory (contiguous 32-bit streams the
+source then widens into read order, or — return_path "direct" — int64 ids in their final place); the ordering between GPUs
 is device-side flags in peer memory (csrc/part_session.cu), so the only collectives of a batch are the agreement on the
-number of sub-batches and one all-reduce of the counters. `enable_fused(mode="stream")` keeps round 1's variant (32-bit id
-streams + a scatter pass at the source, a counter all-to-all per sub-batch) for comparison. `query_reads` is the plain
+number of sub-batches and one all-reduce of the counters. `enable_fused(mode="legacy")` keeps round 1's Python pipeline
+(a counter all-to-all per sub-batch) for comparison. `query_reads` is the plain
 formulation (NCCL all-to-all of (canon, minimizer) out and ids back), kept as the fallback when an inbox overflows and as
 the path the CPU `gloo` tests drive.
 
@@ -232,18 +233,19 @@ class PartitionedSet:
         del self._inbox, self._ret, self._side
 
     def enable_fused(self, want_ids: bool = True, sub_positions: int = 64 << 20, records_per_position: Optional[float] = None,
-                     ids_capacity: int = 0, mode: Optional[str] = None, order: Optional[str] = None):
+                     ids_capacity: int = 0, mode: Optional[str] = None, order: Optional[str] = None, return_path: Optional[str] = None):
         """Allocates and exchanges the peer buffers. mode "session" (default): csrc/part_session.cu — per rank a double
         buffered inbox of world regions of `cap` records (written by the sources), a mailbox of flags, and for the id mode
-        an id array of `ids_capacity` int64 (written by the owners; grown on demand by query_reads_fused). mode "stream":
-        round 1's variant — return area of world regions of `sub_positions` 32-bit ids plus the local side table.
+        an id array of `ids_capacity` int64 (grown on demand by query_reads_fused) plus, on the default "stream" return_path,
+        return regions of 32-bit ids and a side table ("direct": the owners store int64 ids straight into the id array).
+        mode "legacy": round 1's Python pipeline (one NCCL all-to-all of the record counts per sub-batch), kept for comparison.
         sub_positions = base positions per sub-batch (one dispatch and one lookup kernel each)."""
         self.disable_fused()
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         dev = torch.device("cuda", self.index.device)
-        mode = mode or os.environ.get("BLIGHT_PART_RETURN", "session")
-        if mode != "stream":
+        mode = mode or os.environ.get("BLIGHT_PART_PIPELINE", "session")
+        if mode != "legacy":
             if records_per_position is None:
                 records_per_position = min(0.25, max(0.03, 0.5 / world))
             max_cap = (1 << 24) - 1
@@ -253,6 +255,7 @@ class PartitionedSet:
             self._world, self._rank, self._fused_ids = world, rank, want_ids
             self._session_args = (world, rank)
             self._order = order or os.environ.get("BLIGHT_PART_ORDER") or DEFAULT_ORDER  # "serial" | "ahead" | "overlap"
+            self._return_path = return_path  # None: BLIGHT_PART_RETURN or "stream"
             self._make_session(int(ids_capacity) if want_ids else 0)
             return
         if records_per_position is None:
@@ -331,16 +334,16 @@ class PartitionedSet:
             self._session.close()
         dev = torch.device("cuda", self.index.device)
         self._session = api.PartSession(self.index, world, rank, self.plan.lb, self.plan.cuts, self._sub, self._cap, ids_capacity,
-                                        order=self._order)
+                                        order=self._order, return_path=self._return_path)
         everyone = [None] * world
-        mine = (self._session.handles(), ids_capacity)
+        mine = (self._session.handles(), ids_capacity, int(self.index.info["id_base"]))
         if world > 1:
             dist.all_gather_object(everyone, mine, group=self.group)
         else:
             everyone = [mine]
-        for r, (h, cap_r) in enumerate(everyone):
+        for r, (h, cap_r, base_r) in enumerate(everyone):
             if r != rank:
-                self._session.connect_ipc(r, h, cap_r)
+                self._session.connect_ipc(r, h, cap_r, base_r)
         self._ids_view = self._session.ids_tensor(dev)
         self._err_seen = 0
         if world > 1:

@@ -80,6 +80,14 @@ int blight_flat_build_seqs(const char* bases, const uint64_t* offsets, uint64_t 
 int blight_flat_build_spans(const char* bases, const uint64_t* starts, const uint64_t* lengths, uint64_t n_seqs,
                             uint32_t k, uint32_t m, uint32_t n_log2, uint32_t s_log2, uint32_t b, uint32_t threads,
                             blight_flat** out);
+/* construct_index ON THE GPU: the same flat image, word for word, as the host builders above (and hence as
+ * the reference with cores=1), built by data-parallel passes on `device` (csrc/gpu_builder.cu). Sequence i =
+ * bases[starts[i] .. starts[i]+lengths[i]) in HOST memory (spans may overlap). The input must be a k-mer SET, as BCALM unitigs
+ * are. *device_seconds (may be NULL) receives the time between the first H2D copy and the last kernel. */
+int blight_flat_build_gpu(const char* bases, const uint64_t* starts, const uint64_t* lengths, uint64_t n_seqs, uint32_t k, uint32_t m,
+                          uint32_t n_log2, uint32_t s_log2, uint32_t b, int device, blight_flat** out, double* device_seconds);
+int blight_flat_build_file_gpu(const char* unitig_path, uint32_t k, uint32_t m, uint32_t n_log2, uint32_t s_log2, uint32_t b, int device,
+                               blight_flat** out);
 /* The reference has no index persistence (only mphf::save/load, bbhash.h:731-775); this is ours. */
 int blight_flat_save(const blight_flat* f, const char* path);
 int blight_flat_load(const char* path, blight_flat** out);
@@ -249,7 +257,12 @@ typedef struct blight_part_config {
 	uint64_t sub_positions;              /* base positions per sub-batch (multiple of 256, < 2^32) */
 	uint64_t cap;                        /* records per (source, owner) inbox region and sub-batch (< 2^24) */
 	uint64_t ids_capacity;               /* entries of this rank's id array (0: counting mode only) */
+	uint32_t return_path;                /* BLIGHT_PART_RETURN_*: how identifiers travel back to the source */
+	uint32_t reserved;
 } blight_part_config;
+#define BLIGHT_PART_RETURN_DEFAULT 0u /* what BLIGHT_PART_RETURN says (stream | direct), else stream */
+#define BLIGHT_PART_RETURN_STREAM 1u  /* contiguous 32-bit id streams per owner warp + a scatter pass at the source */
+#define BLIGHT_PART_RETURN_DIRECT 2u  /* int64 ids stored by the owner straight into the source's id array */
 #define BLIGHT_PART_ORDER_DEFAULT 0u /* what BLIGHT_PART_ORDER says (serial | ahead | overlap), else the library's choice */
 #define BLIGHT_PART_ORDER_SERIAL 1u  /* dispatch(i), lookup(i), dispatch(i+1), ... on one stream */
 #define BLIGHT_PART_ORDER_AHEAD 2u   /* dispatch(i+1) before lookup(i) on one stream: the wait for the peers never sees dispatch skew */
@@ -258,9 +271,11 @@ typedef struct blight_part_config {
 #define BLIGHT_PART_TIMEOUT 2u  /* status flag: a peer's flag never arrived */
 int blight_part_session_create(const blight_index* local_slice, const blight_part_config* cfg, blight_part_session** out);
 void blight_part_session_free(blight_part_session* s);
-/* 3 x 64 bytes: CUDA IPC handles of this rank's inbox, mailbox and id array (zeros when there is none). */
-int blight_part_session_handles(const blight_part_session* s, unsigned char* handles192);
-int blight_part_session_connect_ipc(blight_part_session* s, uint32_t peer, const unsigned char* handles192, uint64_t peer_ids_capacity);
+/* 4 x 64 bytes: CUDA IPC handles of this rank's inbox, mailbox, id array and return regions (zeros when there is none). */
+int blight_part_session_handles(const blight_part_session* s, unsigned char* handles256);
+/* peer_id_base: blight_info.id_base of the peer's slice (owners answer with slice-local 32-bit ids on the stream path). */
+int blight_part_session_connect_ipc(blight_part_session* s, uint32_t peer, const unsigned char* handles256, uint64_t peer_ids_capacity,
+                                    uint64_t peer_id_base);
 int blight_part_session_connect_local(blight_part_session* s, uint32_t peer, const blight_part_session* other);
 /* DEVICE pointer of this rank's id array: after a query (and a synchronisation of its stream) slot d_kmer_off[r] + pos holds
  * the identifier query_sequence_hash would return for k-mer pos of read r (blight.cpp:575-591). */
@@ -316,6 +331,8 @@ int blight_fasta_cut_stream(const char* text, uint64_t len, uint64_t chunk_bytes
 
 /* Bytes the host-buffer entry points copied host->device and device->host in the calling process since load. */
 void blight_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
+/* The host packer of blight_query_reads_host: bases it packed to 2 bits, wall time it spent packing (ns), threads it uses. */
+void blight_host_pack_stats(uint64_t* packed_bases, uint64_t* pack_ns, uint32_t* threads);
 /* Number of kernel launches issued by this library in the calling process (all threads) since load. */
 uint64_t blight_launch_count(void);
 

@@ -18,13 +18,13 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("ret", ["session", "session+ahead", "session+overlap", "stream"])
+@pytest.mark.parametrize("ret", ["stream", "stream+ahead", "stream+overlap", "direct", "legacy"])
 def test_partition_ids_equal_replica_on_real_peers(ret):
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     env = dict(os.environ, BLIGHT_CHECK_GENOME="20000000", BLIGHT_CHECK_READS="400000", BLIGHT_CHECK_SUB=str(8 << 20), BLIGHT_CHECK_REPS="2",
-               BLIGHT_PART_RETURN=ret.split("+")[0])
+               **({"BLIGHT_PART_PIPELINE": "legacy"} if ret == "legacy" else {"BLIGHT_PART_RETURN": ret.split("+")[0]}))
     if "+" in ret:
         env["BLIGHT_PART_ORDER"] = ret.split("+")[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",

@@ -26,13 +26,17 @@ def _dev_batch(torch, rb, ro, k=31):
             torch.from_numpy(koff.astype(np.int64)).cuda(), int(koff[-1]))
 
 
-@pytest.mark.parametrize("mode", ["session", "stream"])
+@pytest.mark.parametrize("mode", ["stream", "direct", "legacy"])
 @pytest.mark.parametrize("shape", [(9, 6, 6), (7, 5, 0), (11, 8, 8)])
 def test_loopback_partition_matches_oracle(shape, mode, tmp_path, torch_cuda, monkeypatch):
-    """mode session: ids stored straight into the source's id array, ordering by device-side flags (part_session.cu);
-    mode stream: round 1's 32-bit return streams + scatter pass."""
+    """stream / direct: the session of part_session.cu (ordering by device-side flags) with its two return paths — 32-bit id
+    streams + scatter pass at the source, or int64 ids stored by the owner straight into the source's id array;
+    legacy: round 1's Python pipeline (a counter all-to-all per sub-batch)."""
     torch = torch_cuda
-    monkeypatch.setenv("BLIGHT_PART_RETURN", mode)
+    if mode == "legacy":
+        monkeypatch.setenv("BLIGHT_PART_PIPELINE", "legacy")
+    else:
+        monkeypatch.setenv("BLIGHT_PART_RETURN", mode)
     m, n, b = shape
     g, ub, uo, rb, ro = common.synthetic(600_000, 6000, seed=11 + m, sub_rate=0.03)
     flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=m, n=n, s=0, b=b, threads=0)
@@ -171,7 +175,7 @@ def test_three_sessions_on_one_gpu(tmp_path, torch_cuda):
     owners = [flat.slice(*plan.group_range(r)).upload(0) for r in range(world)]
     koff_all = synth.kmer_offsets(ro, 31)
     cutsr = [0, 6000, 9000, 9000]  # reads per rank: 6000, 3000, 0
-    for order in ("serial", "ahead", "overlap"):
+    for order, ret in (("serial", "stream"), ("ahead", "stream"), ("overlap", "stream"), ("serial", "direct"), ("overlap", "direct")):
         sub = 1 << 17
         sess, batches = [], []
         for r in range(world):
@@ -180,7 +184,7 @@ def test_three_sessions_on_one_gpu(tmp_path, torch_cuda):
             po = (ro[lo:hi + 1] - ro[lo]) if hi > lo else np.zeros(1, dtype=np.uint64)
             d_b, d_o, d_k, total = _dev_batch(torch, pb, po)
             batches.append((d_b, d_o, d_k, total, want[int(koff_all[lo]):int(koff_all[hi])]))
-            sess.append(api.PartSession(owners[r], world, r, plan.lb, plan.cuts, sub, 1 << 15, max(total, 1), order=order))
+            sess.append(api.PartSession(owners[r], world, r, plan.lb, plan.cuts, sub, 1 << 15, max(total, 1), order=order, return_path=ret))
         for r in range(world):
             for q in range(world):
                 if q != r:
@@ -201,7 +205,7 @@ def test_three_sessions_on_one_gpu(tmp_path, torch_cuda):
                 assert sess[r].status(stream=streams[r]) == 0
                 total, w = batches[r][3], batches[r][4]
                 got = sess[r].ids_tensor("cuda")[:total].cpu().numpy()
-                assert np.array_equal(got, w), (order, rep, r)
+                assert np.array_equal(got, w), (order, ret, rep, r)
             tot = sum(c.cpu().numpy() for c in ctrs)
             assert (int(tot[0]), int(tot[1]), int(tot[2])) == (int(wctr[0]), int(wctr[1]), int(wctr[2]))
         # counting mode

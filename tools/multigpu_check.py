@@ -103,7 +103,7 @@ def main():
     rep_cnt_ms = timed(lambda: rep.index.query_reads(bases, roff, want_ids=False), reps, dev)
     del scratch
 
-    out = {"return_path": os.environ.get("BLIGHT_PART_RETURN", "session") + ("+ahead" if os.environ.get("BLIGHT_PART_ORDER") == "ahead" else ""), "world": world, "index_kmers": N, "reads_per_rank": n_reads, "kmers_per_rank": total, "shape": {"m": m, "n": n, "b": b},
+    out = {"return_path": os.environ.get("BLIGHT_PART_PIPELINE", "session") + ":" + os.environ.get("BLIGHT_PART_RETURN", "stream") + "+" + os.environ.get("BLIGHT_PART_ORDER", "serial"), "world": world, "index_kmers": N, "reads_per_rank": n_reads, "kmers_per_rank": total, "shape": {"m": m, "n": n, "b": b},
            "build_seconds": build_s, "cuts": part.plan.cuts, "replica_index_bytes": rep.index.info["device_bytes"],
            "local_index_bytes": part.index.info["device_bytes"],
            "replica_ids_ms": rep_ids_ms, "replica_ids_kmers_per_s": world * total / (rep_ids_ms * 1e-3),
@@ -125,7 +125,7 @@ def main():
         torch.cuda.synchronize()
         out["fused_ids_equal_replica"] &= bool(okf.item())
         out["fused_counters_equal_replica"] &= bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]) and torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
-        stream_mode = os.environ.get("BLIGHT_PART_RETURN") == "stream"  # the session path answers in its own id array: no copy
+        stream_mode = os.environ.get("BLIGHT_PART_PIPELINE") == "legacy"  # the session path answers in its own id array: no copy
         f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, ids=ids_buf if stream_mode else None, check_overflow=False), reps, dev)
         f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False), reps, dev)
         ovf = torch.tensor([1 if part.overflowed() else 0], device=dev)
