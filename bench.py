@@ -59,12 +59,13 @@ def parse():
     ap.add_argument("--no-file-query", action="store_true")
     ap.add_argument("--ids-only", action="store_true", help="diagnostic: time only the id (hash) mode")
     ap.add_argument("--count-only", action="store_true", help="diagnostic: time only the counting (bool) mode")
+    ap.add_argument("--packed-input", action="store_true", help="diagnostic: the reads are held 2-bit packed on the device (blight_query_reads_packed)")
     ap.add_argument("--compact", action="store_true", help="diagnostic: upload without the derived tables (the reference's arrays only)")
     ap.add_argument("--no-partition", action="store_true", help="N > 1: skip the bucket-partitioned leg")
     ap.add_argument("--partition-genome", type=int, default=1_000_000_000)
     ap.add_argument("--partition-reads", type=int, default=4_000_000, help="reads per GPU per batch of the partitioned leg")
     ap.add_argument("--partition-shape", default="9,10,6", help="m,n,b of the partitioned index")
-    ap.add_argument("--partition-sub", type=int, default=32 << 20, help="base positions per sub-batch of the partitioned leg")
+    ap.add_argument("--partition-sub", type=int, default=128 << 20, help="base positions per sub-batch of the partitioned leg")
     ap.add_argument("--build-blob", default=None, help=argparse.SUPPRESS)  # internal: build the workload index, save it, exit
     return ap.parse_args()
 
@@ -398,8 +399,13 @@ def partition_leg(args, rank, world, local, dev):
 
     del scratch
     variants, same_all, ctr_ok_all, ovf_all = {}, True, True, False
-    for name, order, ret in (("serial", "serial", "stream"), ("ahead", "ahead", "stream"), ("overlap", "overlap", "stream"), ("serial/direct", "serial", "direct")):
-        part.enable_fused(sub_positions=args.partition_sub, ids_capacity=total, order=order, return_path=ret)
+    sub_d = args.partition_sub
+    for name, order, ret, sub in ((f"serial/stream/{sub_d >> 20}M", "serial", "stream", sub_d), ("serial/stream/32M", "serial", "stream", 32 << 20),
+                                  ("serial/stream/256M", "serial", "stream", 256 << 20), (f"ahead/stream/{sub_d >> 20}M", "ahead", "stream", sub_d),
+                                  (f"serial/direct/{sub_d >> 20}M", "serial", "direct", sub_d)):
+        if name in variants:
+            continue
+        part.enable_fused(sub_positions=sub, ids_capacity=total, order=order, return_path=ret)
         ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
         torch.cuda.synchronize()
         same = torch.tensor([1 if torch.equal(ids_f, ids_one) else 0], device=dev)
@@ -417,7 +423,7 @@ def partition_leg(args, rank, world, local, dev):
         same_all &= bool(same.item()); ctr_ok_all &= ctr_ok; ovf_all |= bool(ovf.item())
     del ids_one, whole
     torch.cuda.empty_cache()
-    default_order = bdist.DEFAULT_ORDER
+    default_order = f"serial/stream/{sub_d >> 20}M"
     f_ids_ms, f_cnt_ms = variants[default_order]["ids_ms"], variants[default_order]["counting_ms"]
     local_bytes = part.index.info["device_bytes"]
     part.disable_fused()
@@ -434,7 +440,7 @@ def partition_leg(args, rank, world, local, dev):
                                 "ids_ms": one_ids_ms, "counting_ms": one_cnt_ms, "device_bytes": whole_bytes},
         "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms, "counting_vs_one_gpu": world * one_cnt_ms / f_cnt_ms,
         "ids_equal_replica": same_all, "counters_equal_replica": ctr_ok_all, "overflow": ovf_all,
-        "kernel_order": default_order, "by_kernel_order": variants,
+        "variant": default_order, "variants": variants,
         "device_bytes_per_gpu": local_bytes, "cuts": part.plan.cuts, "sub_positions": part._sub,
         "return_path": "stream: an owner's warp stores its 32-bit ids as one contiguous run into the source's return region, the source widens them into read order one sub-batch behind; ordering between GPUs by device-side flags (csrc/part_session.cu)",
         "build_seconds": build_s, "leg_seconds": time.time() - t_leg,
@@ -487,11 +493,28 @@ def main():
     d_ids = torch.empty(total_kmers, dtype=torch.int64, device=dev)
     d_ctr = torch.zeros(api.N_CTR, dtype=torch.int64, device=dev)
 
+    d_packed = None
+    if args.packed_input:
+        code = ((d_bases >> 1) & 3).to(torch.int64)
+        pad = (-code.numel()) % 16
+        if pad:
+            code = torch.cat([code, torch.zeros(pad, dtype=torch.int64, device=dev)])
+        sh = torch.arange(30, -2, -2, device=dev, dtype=torch.int64)
+        d_packed = ((code.view(-1, 16) << sh).sum(1) & 0xFFFFFFFF).to(torch.int32)  # 16 bases per word, first base in the high bits
+        d_packed = torch.cat([d_packed, torch.zeros(64, dtype=torch.int32, device=dev)])
+        del code
+
     def step_count():
-        idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
+        if d_packed is not None:
+            idx.query_reads_packed(d_packed, d_roff, d_bases.numel(), want_ids=False, ctr=d_ctr)
+        else:
+            idx.query_reads(d_bases, d_roff, want_ids=False, ctr=d_ctr)
 
     def step_ids():
-        idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
+        if d_packed is not None:
+            idx.query_reads_packed(d_packed, d_roff, d_bases.numel(), d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
+        else:
+            idx.query_reads(d_bases, d_roff, d_koff, total_kmers, ids=d_ids, ctr=d_ctr)
 
     def sync_all():
         torch.cuda.synchronize()

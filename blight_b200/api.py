@@ -49,7 +49,7 @@ class PartConfig(C.Structure):
     """blight_part_config (include/blight_b200.h)"""
     _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("lb", C.c_uint32), ("order", C.c_uint32),
                 ("cuts", C.c_uint32 * (MAX_RANKS + 1)), ("sub_positions", C.c_uint64), ("cap", C.c_uint64),
-                ("ids_capacity", C.c_uint64), ("return_path", C.c_uint32), ("reserved", C.c_uint32)]
+                ("ids_capacity", C.c_uint64), ("return_path", C.c_uint32), ("reserved", C.c_uint32), ("ret_kmers", C.c_uint64)]
 
 
 PART_OVERFLOW, PART_TIMEOUT = 1, 2
@@ -583,9 +583,10 @@ class PartSession:
     id array, the peers' buffers, and the per-batch pipeline ordered by device-side flags."""
 
     def __init__(self, index: "DeviceIndex", world: int, rank: int, lb: int, cuts: Sequence[int], sub_positions: int, cap: int,
-                 ids_capacity: int = 0, order: Optional[str] = None, return_path: Optional[str] = None):
+                 ids_capacity: int = 0, order: Optional[str] = None, return_path: Optional[str] = None, ret_kmers: int = 0):
         cfg = PartConfig()
         cfg.return_path = PART_RETURNS[return_path]
+        cfg.ret_kmers = ret_kmers
         cfg.world, cfg.rank, cfg.lb, cfg.sub_positions, cfg.cap, cfg.ids_capacity = world, rank, lb, sub_positions, cap, ids_capacity
         cfg.order = PART_ORDERS[order]
         for i, c in enumerate(cuts):

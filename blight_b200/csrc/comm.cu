@@ -100,6 +100,7 @@ int make_sessions(blight_comm* c, uint64_t sub, uint64_t cap, uint64_t ids_cap) 
 	for (uint32_t g = 0; g < c->n; g++) {
 		blight_part_config cfg{};
 		cfg.world = c->n; cfg.rank = g; cfg.lb = c->lb; cfg.sub_positions = sub; cfg.cap = cap; cfg.ids_capacity = ids_cap;
+		cfg.ret_kmers = c->n <= 2 || cap >= sub ? sub : uint64_t(sub * 2.5 / c->n);  // cap >= sub: the retry after an overflow, sized for the worst case
 		for (uint32_t i = 0; i <= c->n; i++) cfg.cuts[i] = c->cuts[i];
 		int rc = blight_part_session_create(c->idx[g], &cfg, &c->sess[g]);
 		if (rc != BL_OK) return rc;

@@ -66,30 +66,51 @@ int flat_load(const std::string& path, FlatIndex& f, std::string* err) {
 }
 
 int flat_validate(const FlatIndex& f, std::string* err) {
+	// A blob may come from anywhere (load_index, the slices of the partitioned mode): everything the device code later uses
+	// as an index or an extent is checked here, with arithmetic that cannot wrap.
 	const FlatHeader& h = f.h;
 	auto bad = [&](const char* what) { set_err(err, std::string("flat index invalid: ") + what); return BL_ERR_FORMAT; };
+	auto mul_ok = [](uint64_t a, uint64_t b, uint64_t* out) { return !__builtin_mul_overflow(a, b, out); };
+	auto add_ok = [](uint64_t a, uint64_t b, uint64_t* out) { return !__builtin_add_overflow(a, b, out); };
 	if (h.k == 0 || h.k > 31) return bad("k");
 	if ((h.m & 1) == 0 || h.m > 15 || h.m > h.k) return bad("m");
 	if (h.n_log2 > 2 * h.m - 1) return bad("n");
-	if (h.b > 31) return bad("b");
+	if (h.b > 24) return bad("b");  // check_params' limit
 	if (f.bucket_start.size() != h.n_buckets || f.bucket_nuc.size() != h.n_buckets) return bad("bucket table size");
 	if (f.mphf.size() != h.n_mphf) return bad("mphf table size");
-	if (f.seq.size() != h.seq_words || h.seq_words != (h.total_nuc * 2 + 63) / 64) return bad("seq words");
-	if (f.pos.size() != h.pos_words || h.pos_words != (h.positions_bits + 63) / 64) return bad("pos words");
+	uint64_t t = 0;
+	if (!mul_ok(h.total_nuc, 2, &t) || !add_ok(t, 63, &t) || f.seq.size() != h.seq_words || h.seq_words != t / 64) return bad("seq words");
+	if (!add_ok(h.positions_bits, 63, &t) || f.pos.size() != h.pos_words || h.pos_words != t / 64) return bad("pos words");
 	if (f.bits.size() != h.bits_words_total || f.ranks.size() != h.ranks_total) return bad("mphf arrays");
 	if (f.fb_keys.size() != h.fallback_total || f.fb_vals.size() != h.fallback_total) return bad("fallback arrays");
-	for (uint64_t i = 0; i < h.n_buckets; i++)
-		if (f.bucket_start[i] + f.bucket_nuc[i] > h.total_nuc) return bad("bucket extent");
+	// buckets tile the text in order (the upload pass finds a position's bucket by binary search over the starts)
+	for (uint64_t i = 0; i < h.n_buckets; i++) {
+		uint64_t e = 0;
+		if (!add_ok(f.bucket_start[i], f.bucket_nuc[i], &e) || e > h.total_nuc) return bad("bucket extent");
+		if (i + 1 < h.n_buckets && f.bucket_start[i + 1] != e) return bad("bucket starts are not the running sum of the bucket lengths");
+	}
 	for (const MphfRec& r : f.mphf) {
-		if (!r.present) continue;
-		if (r.bits_word_off + r.bits_nwords > h.bits_words_total) return bad("mphf bits extent");
-		if (r.ranks_off + r.nranks > h.ranks_total) return bad("mphf ranks extent");
-		if (r.fb_off + r.fb_count > h.fallback_total) return bad("mphf fallback extent");
 		if (r.nbits == 0 || r.nbits > 32) return bad("mphf nbits");
+		if (!r.present) continue;
+		uint64_t e = 0;
+		if (!add_ok(r.bits_word_off, r.bits_nwords, &e) || e > h.bits_words_total) return bad("mphf bits extent");
+		if (!add_ok(r.ranks_off, r.nranks, &e) || e > h.ranks_total) return bad("mphf ranks extent");
+		if (!add_ok(r.fb_off, r.fb_count, &e) || e > h.fallback_total) return bad("mphf fallback extent");
 		uint64_t tot = 0;
-		for (int l = 0; l < kLevels; l++) { if (r.dom[l] == 0 || (r.dom[l] & 63)) return bad("mphf level domain"); tot += r.dom[l]; }
-		if (tot != r.bits_nwords * 64) return bad("mphf level domains do not sum to the bit array size");
-		if (r.pos_start + r.nelem * r.nbits > h.positions_bits) return bad("mphf positions extent");
+		for (int l = 0; l < kLevels; l++) {
+			if (r.dom[l] == 0 || (r.dom[l] & 63)) return bad("mphf level domain");
+			if (!add_ok(tot, r.dom[l], &tot)) return bad("mphf level domain");
+		}
+		uint64_t nb = 0;
+		if (!mul_ok(r.bits_nwords, 64, &nb) || tot != nb) return bad("mphf level domains do not sum to the bit array size");
+		uint64_t pe = 0;
+		if (!mul_ok(r.nelem, (uint64_t)r.nbits, &pe) || !add_ok(pe, r.pos_start, &pe) || pe > h.positions_bits) return bad("mphf positions extent");
+		// a rank is (ones before a set bit) or a fallback value: both must index the group's position fields
+		uint64_t ones = 0;
+		for (uint64_t w = 0; w < r.bits_nwords; w++) ones += (uint64_t)__builtin_popcountll(f.bits[r.bits_word_off + w]);
+		if (ones > r.nelem) return bad("more level bits set than keys");
+		for (uint64_t j = 0; j < r.fb_count; j++)
+			if (f.fb_vals[r.fb_off + j] >= r.nelem) return bad("fallback rank out of range");
 	}
 	return BL_OK;
 }

@@ -22,7 +22,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -553,6 +556,17 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	};
 	if (n_views == 0) return finish_empty();
 
+	// BLIGHT_BUILD_DEBUG=1: wall clock of every phase on stderr (each mark synchronises the device)
+	const bool dbg = [] { const char* e = getenv("BLIGHT_BUILD_DEBUG"); return e && atoi(e); }();
+	double t_mark = 0;
+	auto mark = [&](const char* what) {
+		if (!dbg) return;
+		cudaDeviceSynchronize();
+		const double t = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+		if (t_mark > 0) fprintf(stderr, "[blight build] %-28s %8.2f ms\n", what, 1e3 * (t - t_mark));
+		t_mark = t;
+	};
+	mark("start");
 	Arena A;
 	Scan S;
 	cudaEvent_t ev0, ev1;
@@ -578,6 +592,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	CU(cudaMemcpy(d_vstart, vstart.data(), (n_views + 1) * 8, cudaMemcpyHostToDevice));
 	CU(cudaMemset(d_key, 0xFF, (total_v + 64) * 4));
 
+	mark("alloc + H2D");
 	// 1. chop
 	const unsigned gv = grid_for(total_v, kT * 4);
 	k_codes<<<gv, kT>>>(d_text, d_starts, d_vstart, n_views, total_v, d_codes, d_rem, d_err);
@@ -586,6 +601,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	k_flags<<<gv, kT>>>(d_kmin, d_rem, total_v, k, d_flag);
 	g_launches += 4;
 	CU(cudaGetLastError());
+	mark("chop kernels");
 	uint32_t h_err = 0;
 	CU(cudaMemcpy(&h_err, d_err, 4, cudaMemcpyDeviceToHost));
 	if (h_err) { set_err("Invalid char in DNA"); return BL_ERR_INVALID_BASE; }
@@ -608,6 +624,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	CU(cudaGetLastError());
 	A.release(d_kmin); A.release(d_flag); A.release(d_skidx);
 
+	mark("super-k-mer records");
 	// bucket table
 	std::vector<uint64_t> bnuc(H.n_buckets), bkm(H.n_buckets);
 	CU(cudaMemcpy(bnuc.data(), d_bnuc, H.n_buckets * 8, cudaMemcpyDeviceToHost));
@@ -629,6 +646,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	AL(d_bucket_start, H.n_buckets);
 	CU(cudaMemcpy(d_bucket_start, F.bucket_start.data(), H.n_buckets * 8, cudaMemcpyHostToDevice));
 
+	mark("bucket table (D2H + host)");
 	// 2. order: stable radix sort by minimizer, 8 bits per pass
 	uint32_t *d_ka, *d_kb, *d_va, *d_vb, *d_ghist; uint64_t* d_goff;
 	const uint64_t n_tiles = (n_sk + kRadixTile - 1) / kRadixTile;
@@ -658,6 +676,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	if ((rc = exclusive_scan(A, S, d_len_sorted, n_sk, d_dest, nullptr)) != BL_OK) { set_err(g_last_error); return rc; }
 	if ((rc = exclusive_scan(A, S, d_nk_sorted, n_sk, d_keybase, nullptr)) != BL_OK) { set_err(g_last_error); return rc; }
 
+	mark("radix sort + prefix sums");
 	// MPHF group descriptors (blight.cpp:280-306) and level domains
 	F.mphf.assign(H.n_mphf, MphfRec{});
 	std::vector<GroupDev> groups(H.n_mphf);
@@ -700,6 +719,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	CU(cudaMemcpy(d_groups, groups.data(), H.n_mphf * sizeof(GroupDev), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(d_gblock_first, gblock_first.data(), (H.n_mphf + 1) * 8, cudaMemcpyHostToDevice));
 
+	mark("group descriptors (host)");
 	// 3. bucket sequences
 	uint64_t* d_seq;
 	AL(d_seq, H.seq_words + 1);
@@ -716,6 +736,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	g_launches++;
 	CU(cudaGetLastError());
 
+	mark("bucket text + keys");
 	// 4. BBHash, all groups level by level
 	const uint64_t n_words32 = total_bits / 32;
 	uint32_t *d_bits, *d_coll, *d_gcoll, *d_flevel; uint64_t *d_la, *d_lb; unsigned long long* d_nnext;
@@ -751,6 +772,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 		std::sort(leftovers.begin(), leftovers.end());  // key order of the reference's iteration
 	}
 
+	mark("BBHash levels");
 	// 5. ranks
 	uint32_t* d_blockpop; uint64_t *d_bscan, *d_ranks;
 	AL(d_blockpop, total_blocks + 1);
@@ -765,6 +787,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 		g_launches++;
 	}
 
+	mark("ranks");
 	// 6. positions
 	unsigned long long* d_pos;
 	AL(d_pos, H.pos_words + 1, true);
@@ -773,6 +796,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(ev1, 0));
 
+	mark("positions");
 	// export
 	F.seq.assign(H.seq_words, 0);
 	F.pos.assign(H.pos_words, 0);
@@ -786,6 +810,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	CU(cudaMemcpy(flevel.data(), d_flevel, H.n_mphf * 4, cudaMemcpyDeviceToHost));
 	if (seconds_device) { float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); *seconds_device = ms * 1e-3; }
 
+	mark("export D2H");
 	// leftovers by group (they are sorted by key index, groups are contiguous key ranges)
 	std::vector<uint64_t> key_begin(H.n_mphf + 1, 0);
 	for (uint64_t g = 0; g < H.n_mphf; g++) key_begin[g + 1] = key_begin[g] + F.mphf[g].nelem;
@@ -806,22 +831,23 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 			// ones in the whole bit array of the group = the rank the first leftover gets
 			uint64_t cur = 0;
 			for (uint64_t w = 0; w < G.n_words; w++) cur += (uint64_t)__builtin_popcountll(F.bits[R.bits_word_off + w]);
+			// `fm[key] = cur++` in key order (bbhash.h:709-728): a k-mer present twice keeps the LAST rank handed to it, and every
+			// occurrence then writes its offset to that rank's field, later writes winning (blight.cpp:486-519)
 			std::unordered_map<uint64_t, uint64_t> fm;
-			std::vector<std::pair<uint64_t, uint32_t>> placed;  // (rank, offset in bucket)
+			std::vector<std::pair<uint64_t, uint32_t>> seen;  // (key, offset in bucket) of every leftover, in order
 			for (; li < leftovers.size() && leftovers[li] < key_begin[g + 1]; li++) {
 				uint64_t key = 0; uint32_t off = 0;
 				CU(cudaMemcpy(&key, d_keys + leftovers[li], 8, cudaMemcpyDeviceToHost));
 				CU(cudaMemcpy(&off, d_koff + leftovers[li], 4, cudaMemcpyDeviceToHost));
-				fm[key] = cur;
-				placed.emplace_back(cur, off);
-				cur++;
+				fm[key] = cur++;
+				seen.emplace_back(key, off);
 			}
 			std::vector<std::pair<uint64_t, uint64_t>> fb(fm.begin(), fm.end());
 			std::sort(fb.begin(), fb.end());
 			for (auto& kv : fb) { F.fb_keys.push_back(kv.first); F.fb_vals.push_back(kv.second); }
 			R.fb_count = fb.size();
-			for (auto& pr : placed)
-				if (pr.second) host_write_field(F.pos, R.pos_start + pr.first * R.nbits, R.nbits, ((uint64_t)pr.second >> b) & (R.nbits >= 64 ? ~0ull : ((1ull << R.nbits) - 1)));
+			for (auto& ko : seen)
+				if (ko.second) host_write_field(F.pos, R.pos_start + fm[ko.first] * R.nbits, R.nbits, ((uint64_t)ko.second >> b) & (R.nbits >= 64 ? ~0ull : ((1ull << R.nbits) - 1)));
 		}
 	}
 	H.bits_words_total = F.bits.size();

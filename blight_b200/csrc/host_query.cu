@@ -7,6 +7,10 @@
 //   front  (the calling thread)   chunk 0, 1, 2, ...  as ASCII, straight from the caller's buffer, at most two copies queued
 //   back   (a second thread)      chunk n-1, n-2, ... packed to 2 bits per base by the host cores first (host_pack.cpp)
 //
+// Both enqueue their copies on ONE copy stream: with a stream each, the DMA engine served the front's never-empty queue and
+// let the back's copies wait until the very end (measured: 4 of 47 chunks packed, 25 ms of the back thread spent waiting
+// for its first staging buffer). In one stream a packed copy waits for at most the two raw copies queued before it.
+//
 // They meet wherever the PCIe link and the packer cores balance: on a box where one GPU has a whole x16 link and little
 // else to do with its cores, most bytes travel raw; on a box where 8 GPUs share links and cores, the mix shifts by itself.
 // A chunk holding a byte nuc2int rejects (kmer.h:68) is never packed — it travels as ASCII so that the kernel applies the
@@ -22,6 +26,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -222,7 +227,12 @@ Window window_of(const uint64_t* beg, uint64_t n, uint64_t c0, uint64_t upto) {
 	return Window{lo, hi};
 }
 
+// BLIGHT_HOST_DEBUG=1: one line per call on stderr — chunks and host time of either producer
+struct ProducerStats { int chunks = 0; double t_sync = 0, t_pack = 0, t_enqueue = 0; };
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 struct Plan {
+	ProducerStats sf, sb;
 	const blight_index* idx;
 	HostCtx* C;
 	const char* text; uint64_t len;
@@ -270,12 +280,17 @@ int front_producer(Plan& P) {
 		const int c = P.claim_front();
 		if (c < 0) return BL_OK;
 		cudaEvent_t ev = C.ev_f[nf & 1];
+		double t0 = now_s();
 		if (nf >= 2) CU(cudaEventSynchronize(ev));  // at most two raw copies queued: the back producer gets its share of the link
+		P.sf.t_sync += now_s() - t0;
+		t0 = now_s();
 		const uint64_t c0 = P.cut[c], upto = std::min(P.len, P.cut[c + 1] + kHalo);
 		CU(cudaMemcpyAsync(P.d_text + c0, P.text + c0, upto - c0, cudaMemcpyHostToDevice, C.cs_raw));
 		g_h2d_bytes += upto - c0;
 		const int rc = window_and_launch(P, c, false, C.cs_raw, ev, C.st_f);
 		if (rc != BL_OK) return rc;
+		P.sf.t_enqueue += now_s() - t0;
+		P.sf.chunks++;
 	}
 }
 
@@ -285,22 +300,28 @@ int back_producer(Plan& P) {
 		const int c = P.claim_back();
 		if (c < 0) return BL_OK;
 		const int s = nb % kSlots;
+		double ts = now_s();
 		if (nb >= kSlots) CU(cudaEventSynchronize(C.ev_slot[s]));  // the copy that last read this staging buffer has left
+		P.sb.t_sync += now_s() - ts;
 		const uint64_t c0 = P.cut[c], upto = std::min(P.len, P.cut[c + 1] + kHalo);
 		const uint64_t n_bases = upto - c0, n_words = (n_bases + 15) / 16;
 		const auto t0 = std::chrono::steady_clock::now();
 		const bool bad = !C.pool->run(P.text + c0, n_bases, C.stage[s]);
 		g_pack_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+		P.sb.t_pack += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		ts = now_s();
 		if (!bad) {
 			g_packed_bases += n_bases;
-			CU(cudaMemcpyAsync(P.d_packed + (c0 >> 4), C.stage[s], n_words * 4, cudaMemcpyHostToDevice, C.cs_pk));
+			CU(cudaMemcpyAsync(P.d_packed + (c0 >> 4), C.stage[s], n_words * 4, cudaMemcpyHostToDevice, C.cs_raw));
 			g_h2d_bytes += n_words * 4;
 		} else {
-			CU(cudaMemcpyAsync(P.d_text + c0, P.text + c0, n_bases, cudaMemcpyHostToDevice, C.cs_pk));
+			CU(cudaMemcpyAsync(P.d_text + c0, P.text + c0, n_bases, cudaMemcpyHostToDevice, C.cs_raw));
 			g_h2d_bytes += n_bases;
 		}
-		const int rc = window_and_launch(P, c, !bad, C.cs_pk, C.ev_slot[s], C.st_b);
+		const int rc = window_and_launch(P, c, !bad, C.cs_raw, C.ev_slot[s], C.st_b);
 		if (rc != BL_OK) return rc;
+		P.sb.t_enqueue += now_s() - ts;
+		P.sb.chunks++;
 	}
 }
 
@@ -373,8 +394,14 @@ int host_query_records(const blight_index* idx, const char* text, uint64_t len, 
 	}
 	rc = front_producer(P);
 	if (back.joinable()) back.join();
+	if (const char* e = getenv("BLIGHT_HOST_DEBUG")) {
+		if (atoi(e))
+			fprintf(stderr, "[blight host] %zu chunks: front %d (sync %.2f ms, enqueue %.2f ms)  back %d (sync %.2f ms, pack %.2f ms, enqueue %.2f ms)  threads %d\n",
+			        P.cut.size() - 1, P.sf.chunks, 1e3 * P.sf.t_sync, 1e3 * P.sf.t_enqueue, P.sb.chunks, 1e3 * P.sb.t_sync, 1e3 * P.sb.t_pack,
+			        1e3 * P.sb.t_enqueue, threads);
+	}
 	if (rc == BL_OK && rc_back != BL_OK) rc = fail(rc_back, err_back);
-	if (rc != BL_OK) { cudaStreamSynchronize(C.st_f); cudaStreamSynchronize(C.st_b); cudaStreamSynchronize(C.cs_raw); cudaStreamSynchronize(C.cs_pk); return rc; }
+	if (rc != BL_OK) { cudaStreamSynchronize(C.st_f); cudaStreamSynchronize(C.st_b); cudaStreamSynchronize(C.cs_raw); cudaStreamSynchronize(C.cs_raw); return rc; }
 	CU(cudaEventRecord(C.ev_join, C.st_b));
 	CU(cudaStreamWaitEvent(C.st_f, C.ev_join, 0));
 	if (ids_out && total_kmers) { CU(cudaMemcpyAsync(ids_out, P.d_ids, total_kmers * 8, cudaMemcpyDeviceToHost, C.st_f)); g_d2h_bytes += total_kmers * 8; }

@@ -224,13 +224,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 			if (b0 < n_load) {
 				const uint4 v = (aligned16 && b0 + 16 <= n_load) ? __ldcs(reinterpret_cast<const uint4*>(bases + t0 + b0))  // t0 % 256 == 0
 				                                                  : load16_slow(bases + t0 + b0, n_load - b0);
-				unsigned char ch[16];
-				*reinterpret_cast<uint4*>(ch) = v;
+				const uint32_t q4[4] = {nuc_code4(v.x), nuc_code4(v.y), nuc_code4(v.z), nuc_code4(v.w)};
 				#pragma unroll
-				for (int j = 0; j < 16; j++) {
-					const uint32_t c = nuc_code(ch[j]);
-					badw = (badw << 1) | (c >> 2);
-					word = (word << 2) | (c & 3u);
+				for (int j = 0; j < 4; j++) {
+					word = (word << 8) | (q4[j] & 0xFFu);
+					badw = (badw << 4) | (q4[j] >> 8);
 				}
 			}
 			pack[lane] = word;

@@ -23,6 +23,21 @@ BL_HD uint32_t nuc_code(unsigned char c) {
 	return ok ? ((c >> 1) & 3u) : 4u;
 }
 
+#if defined(__CUDACC__)
+// Four ASCII bases at once (one 32-bit word of the text, first base in the low byte): their 2-bit codes packed first base
+// high in the low 8 bits of the result, and in bits 8..11 one flag per base (bit 11 = first) for bytes nuc2int rejects.
+// Byte-wise SIMD compares instead of 4 x (fold case, 4 compares): the front end's phase A drops from ~10 to ~3
+// instructions per base.
+__device__ __forceinline__ uint32_t nuc_code4(uint32_t w) {
+	const uint32_t u = w & 0xDFDFDFDFu;  // fold case
+	const uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+	const uint32_t c = (w >> 1) & 0x03030303u;
+	const uint32_t codes = (c * 0x40100401u) >> 24;                // b0 b1 b2 b3 -> one byte, first base in the high bits
+	const uint32_t bad = ((~ok & 0x01010101u) * 0x08040201u) >> 24;  // one bit per byte, first base -> bit 3
+	return codes | ((bad & 0xFu) << 8);
+}
+#endif
+
 BL_HD uint64_t bitrev64(uint64_t x) {
 #if defined(__CUDA_ARCH__)
 	return __brevll(x);

@@ -97,6 +97,7 @@ struct blight_part_session {
 	int device = 0;
 	blight_part_config cfg{};
 	uint64_t region_bytes = 0;
+	uint64_t kcap = 0;  // ids per (owner, sub-batch) return region
 	// this rank's peer-visible buffers
 	void* inbox = nullptr;     // [2][world sources][cap] records
 	Mailbox* mail = nullptr;
@@ -147,6 +148,7 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	blight_part_session* s = new blight_part_session();
 	s->idx = idx; s->device = idx->device; s->cfg = *cfg;
 	s->region_bytes = cfg->cap * BLIGHT_RUN_RECORD_BYTES;
+	s->kcap = cfg->ret_kmers && cfg->ret_kmers < cfg->sub_positions ? cfg->ret_kmers : cfg->sub_positions;
 	s->order = cfg->order;
 	if (s->order == BLIGHT_PART_ORDER_DEFAULT) {
 		s->order = BLIGHT_PART_ORDER_SERIAL;
@@ -171,7 +173,7 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	if (e == cudaSuccess) e = cudaMemset(s->mail, 0, sizeof(Mailbox));
 	if (e == cudaSuccess && cfg->ids_capacity) e = cudaMalloc(reinterpret_cast<void**>(&s->ids), (size_t)cfg->ids_capacity * 8);
 	if (e == cudaSuccess && cfg->ids_capacity && s->stream_ret) {
-		e = cudaMalloc(reinterpret_cast<void**>(&s->ret), (size_t)2 * cfg->world * cfg->sub_positions * 4);
+		e = cudaMalloc(reinterpret_cast<void**>(&s->ret), (size_t)2 * cfg->world * s->kcap * 4);
 		if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->side), (size_t)2 * cfg->world * cfg->cap * sizeof(uint4));
 	}
 	for (int b = 0; b < 2 && e == cudaSuccess; b++) {
@@ -181,9 +183,12 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	}
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->err), 4);
 	if (e == cudaSuccess) e = cudaMemset(s->err, 0, 4);
-	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side_st, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming);
+	// extra streams only for who needs them: several ranks on ONE device (tests) share its few hardware queues, and a
+	// spinning wait kernel queued in front of another rank's dispatch would never see its flag
+	if (e == cudaSuccess && s->order == BLIGHT_PART_ORDER_OVERLAP) e = cudaStreamCreateWithFlags(&s->side_st, cudaStreamNonBlocking);
+	if (e == cudaSuccess && s->stream_ret && cfg->ids_capacity) e = cudaStreamCreateWithFlags(&s->scat_st, cudaStreamNonBlocking);
+	for (cudaEvent_t* ev : {&s->ev_main, &s->ev_side, &s->ev_pub, &s->ev_scat[0], &s->ev_scat[1]})
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
 	if (e != cudaSuccess) { blight_part_session_free(s); return cu_fail(e, "partition session buffers"); }
 	// a rank is its own peer
 	const uint32_t r = cfg->rank;
@@ -324,13 +329,13 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 	for (int b = 0; b < 2; b++) {
 		blight_part_route& rt = routes[b];
 		std::memset(&rt, 0, sizeof rt);
-		rt.world = world; rt.rank = c.rank; rt.lb = c.lb; rt.cap = c.cap; rt.kcap = c.sub_positions;
+		rt.world = world; rt.rank = c.rank; rt.lb = c.lb; rt.cap = c.cap; rt.kcap = s->kcap;
 		rt.side = stream_ret ? static_cast<void*>(s->side + (size_t)b * world * c.cap) : nullptr;
 		for (uint32_t i = 0; i <= world; i++) rt.cuts[i] = c.cuts[i];
 		for (uint32_t d = 0; d < world; d++) {
 			rt.inbox[d] = static_cast<char*>(s->p_inbox[d]) + ((size_t)b * world + c.rank) * s->region_bytes;  // [half b][source = me] at owner d
 			regions[b][d] = static_cast<const char*>(s->inbox) + ((size_t)b * world + d) * s->region_bytes;   // [half b][source d] here
-			ret_at[b][d] = stream_ret ? static_cast<void*>(s->p_ret[d] + ((size_t)b * world + c.rank) * c.sub_positions) : nullptr;  // [half b][owner = me] at source d
+			ret_at[b][d] = stream_ret ? static_cast<void*>(s->p_ret[d] + ((size_t)b * world + c.rank) * s->kcap) : nullptr;  // [half b][owner = me] at source d
 		}
 	}
 	MailPtrs mp{};
@@ -369,7 +374,7 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 		const int b = (int)(i & 1);
 		return blight_part_lookup_direct(s->idx, world, regions[b], reinterpret_cast<const uint64_t*>(s->rcv[b]), stream_ret ? ret_at[b] : nullptr,
 		                                 want_ids && !stream_ret ? out_ids : nullptr, want_ids && !stream_ret ? s->p_ids_cap : nullptr, c.cap,
-		                                 c.sub_positions, d_ctr, on);
+		                                 s->kcap, d_ctr, on);
 	};
 	auto lookup = [&](uint64_t i) -> int { return lookup_on(i, st); };
 	// stream return: sub-batch i's ids into the id array, on the scatter stream, once the main stream has passed a point
@@ -380,7 +385,7 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 		CU(cudaEventRecord(s->ev_pub, st));
 		CU(cudaStreamWaitEvent(s->scat_st, s->ev_pub, 0));
 		int rc = blight_part_scatter(s->side + (size_t)b * world * c.cap, c.cap, reinterpret_cast<const uint64_t*>(s->counts[b]),
-		                             s->ret + (size_t)b * world * c.sub_positions, c.sub_positions, world, (uint64_t)world * c.cap, s->id_base, s->ids,
+		                             s->ret + (size_t)b * world * s->kcap, s->kcap, world, (uint64_t)world * c.cap, s->id_base, s->ids,
 		                             s->scat_st);
 		if (rc != BL_OK) return rc;
 		CU(cudaEventRecord(s->ev_scat[b], s->scat_st));

@@ -333,8 +333,10 @@ class PartitionedSet:
                 dist.barrier(group=self.group)
             self._session.close()
         dev = torch.device("cuda", self.index.device)
+        # a sub-batch spreads its k-mers over `world` owners: return regions of 2.5 / world of it (an overflow is detected)
+        ret_kmers = self._sub if world <= 2 else int(self._sub * 2.5 / world)
         self._session = api.PartSession(self.index, world, rank, self.plan.lb, self.plan.cuts, self._sub, self._cap, ids_capacity,
-                                        order=self._order, return_path=self._return_path)
+                                        order=self._order, return_path=self._return_path, ret_kmers=ret_kmers)
         everyone = [None] * world
         mine = (self._session.handles(), ids_capacity, int(self.index.info["id_base"]))
         if world > 1:

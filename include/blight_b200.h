@@ -259,6 +259,8 @@ typedef struct blight_part_config {
 	uint64_t ids_capacity;               /* entries of this rank's id array (0: counting mode only) */
 	uint32_t return_path;                /* BLIGHT_PART_RETURN_*: how identifiers travel back to the source */
 	uint32_t reserved;
+	uint64_t ret_kmers;                  /* stream return: ids per (owner, sub-batch) region; 0 = sub_positions (can never overflow);
+	                                        smaller saves memory, a sub-batch sending one owner more raises BLIGHT_PART_OVERFLOW */
 } blight_part_config;
 #define BLIGHT_PART_RETURN_DEFAULT 0u /* what BLIGHT_PART_RETURN says (stream | direct), else stream */
 #define BLIGHT_PART_RETURN_STREAM 1u  /* contiguous 32-bit id streams per owner warp + a scatter pass at the source */

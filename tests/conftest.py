@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Some tests run several ranks of the partitioned path on ONE device (separate streams, ordering by spinning flag kernels):
+# every stream needs a hardware queue of its own, or a wait kernel queued in front of another rank's dispatch never ends.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -150,3 +150,29 @@ def test_fresh_synthetic_equals_reference(tmp_path):
         ours = api.FlatIndex.build_file(fa, 31, m, n, s, b, 4)
         theirs = api.FlatIndex.load(rp)
         assert ours.equals(theirs), ours.difference(theirs)
+
+
+def test_corrupted_blobs_are_refused(tmp_path):
+    """flat_validate: what the device code later indexes with must be in range — bucket starts that are not the running
+    sum of the lengths, level bits that would rank past the group's keys, b beyond the constructor's limit."""
+    a = common.build_lambda(7, 5, 3, 6)
+    p = os.path.join(str(tmp_path), "ok.blflat")
+    a.save(p)
+    raw = np.fromfile(p, dtype=np.uint8)
+    text, bstart, bnuc, h = common.read_blob_text(p)
+    first = int(np.nonzero(bnuc)[0][1])  # a non-empty bucket that is not the first
+    for what in ("bucket_start", "level_bits", "b"):
+        bad = raw.copy()
+        if what == "bucket_start":
+            bad[128 + 8 * first:128 + 8 * first + 8].view(np.uint64)[0] += 1
+        elif what == "b":
+            bad[8 + 16:8 + 20].view(np.uint32)[0] = 25
+        else:
+            off = 128 + 8 * h["n_buckets"] + (4 * h["n_buckets"] + 7) // 8 * 8 + h["n_mphf"] * 208 + 8 * h["seq_words"]
+            pos_words = int(raw[40:128].view(np.uint64)[7])
+            bits0 = off + 8 * pos_words
+            bad[bits0:bits0 + 4096] = 0xFF  # far more ones than the first group has keys
+        q = os.path.join(str(tmp_path), what + ".blflat")
+        bad.tofile(q)
+        with pytest.raises(api.BlightError):
+            api.FlatIndex.load(q)

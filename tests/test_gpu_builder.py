@@ -59,7 +59,7 @@ def test_small_gpu_build_equals_reference_export(shape, tmp_path):
     assert _sha(p) == ANS["small"][f"m{m}_n{n}_b{b}"]["blob_sha256"]
 
 
-@pytest.mark.parametrize("shape", [(31, 7, 5, 6), (31, 9, 12, 2), (31, 11, 8, 8), (31, 15, 20, 5), (31, 5, 0, 3), (21, 7, 4, 4), (16, 5, 3, 2), (25, 11, 8, 6),
+@pytest.mark.parametrize("shape", [(31, 7, 5, 6), (31, 9, 12, 2), (31, 11, 8, 8), (31, 13, 16, 5), (31, 5, 0, 3), (21, 7, 4, 4), (16, 5, 3, 2), (25, 11, 8, 6),
                                    (31, 3, 2, 0)])
 def test_gpu_build_equals_host_build(shape, tmp_path):
     """Overlapping spans of one genome (how the benchmark feeds unitigs), tiny and huge bucket counts, other k, sequences
