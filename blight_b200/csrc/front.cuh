@@ -162,6 +162,7 @@ struct StripSmem {
 	uint32_t* bad;     // [kStripWords]  1 bit per base (bit 15-j of word i = base 16i+j): not ACGTacgt
 	uint32_t* keys;    // [kKeySlots]    ordering key of the m-mer at strip position q, at kidx(q)
 	uint16_t* run_q;   // [kMaxRuns]     strip position of the run's first k-mer
+	uint32_t* run_key; // [kMaxRuns]     ordering key of the run's minimizer (mini_from_key gives the bucket)
 	uint64_t* run_o;   // [kMaxRuns]     output slot of the run's first k-mer (WANT_O)
 	uint64_t* runid8;  // [kStrip / 8]   run of every strip position, one byte each (kTagNone / kTagOverflow)
 };
@@ -281,6 +282,12 @@ __device__ __forceinline__ uint32_t strip_front(const StripSmem& S, uint32_t lan
 		if (WANT_O) {
 			c2.r = rc_.r - (r_last - r_first);
 			c2.load(read_off, read_end);
+		}
+		// the run's minimizer is known here (kmin[] stays in registers: static indices only) and is never recomputed
+		#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const uint32_t id = run_base + __popc(bnd & ((1u << j) - 1u));
+			if (((bnd >> j) & 1u) && id < (uint32_t)kMaxRuns) S.run_key[id] = kmin[j];
 		}
 		uint32_t id = run_base;
 		#pragma unroll 1

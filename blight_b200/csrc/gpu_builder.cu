@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -48,23 +49,96 @@ int cu_fail(cudaError_t e, const char* what) { return fail(BL_ERR_CUDA, std::str
 
 unsigned grid_for(uint64_t n, uint64_t per_block = kT) { return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + per_block - 1) / per_block, 1u << 30)); }
 
-// every device buffer of one build, freed together
+// Every device buffer of one build, carved out of a few large slabs: a build needs ~40 buffers of up to a GB, and one
+// cudaMalloc / cudaFree per buffer cost it tens to hundreds of milliseconds of driver time (measured 5 - 350 ms per phase;
+// the stream-ordered pool was worse: 0.8 - 1.2 s while the pool grew). hint() announces what the next phase will ask for.
 struct Arena {
-	std::vector<void*> ptrs;
+	struct Slab { char* p; size_t cap, used; };
+	std::vector<Slab> slabs;
+	size_t next_hint = 0;
+	void hint(size_t bytes) { next_hint = bytes + bytes / 16 + (1u << 20); }
 	template <class T> int alloc(T** p, uint64_t n, bool zero = false) {
-		void* q = nullptr;
-		const size_t bytes = std::max<size_t>(size_t(n) * sizeof(T), 256);
-		cudaError_t e = cudaMalloc(&q, bytes);
-		if (e != cudaSuccess) return fail(BL_ERR_NOMEM, std::string("cudaMalloc(GPU builder): ") + cudaGetErrorString(e));
-		if (zero && (e = cudaMemset(q, 0, bytes)) != cudaSuccess) { cudaFree(q); return cu_fail(e, "cudaMemset"); }
-		ptrs.push_back(q);
+		const size_t bytes = (std::max<size_t>(size_t(n) * sizeof(T), 256) + 255) & ~size_t(255);
+		if (slabs.empty() || slabs.back().used + bytes > slabs.back().cap) {
+			const size_t cap = std::max(bytes, next_hint);
+			void* q = nullptr;
+			cudaError_t e = cudaMalloc(&q, cap);
+			if (e != cudaSuccess) return fail(BL_ERR_NOMEM, std::string("cudaMalloc(GPU builder): ") + cudaGetErrorString(e));
+			slabs.push_back(Slab{static_cast<char*>(q), cap, 0});
+			next_hint = 0;
+		}
+		Slab& S = slabs.back();
+		void* q = S.p + S.used;
+		S.used += bytes;
+		if (zero) { cudaError_t e = cudaMemsetAsync(q, 0, bytes, 0); if (e != cudaSuccess) return cu_fail(e, "cudaMemset"); }
 		*p = static_cast<T*>(q);
 		return BL_OK;
 	}
-	void release(void* p) {
-		for (auto& q : ptrs) if (q == p) { cudaFree(q); q = nullptr; }
+	void release(void*) {}  // slabs go together
+	~Arena() { for (Slab& S : slabs) cudaFree(S.p); }
+};
+
+// Pageable host memory <-> device through two pinned bounce buffers, the host side of every chunk copied by all cores while
+// the DMA engine moves the previous one (a plain cudaMemcpy on pageable memory ran at 3.5 - 4.5 GB/s: 100 ms for the image).
+struct Bounce {
+	static constexpr size_t kChunk = 64u << 20;
+	char* buf[2] = {nullptr, nullptr};
+	cudaEvent_t ev[2] = {nullptr, nullptr};
+	cudaStream_t st = nullptr;
+	int threads = 1;
+	bool ok = false;
+	Bounce() {
+		ok = cudaHostAlloc(reinterpret_cast<void**>(&buf[0]), kChunk, cudaHostAllocDefault) == cudaSuccess &&
+		     cudaHostAlloc(reinterpret_cast<void**>(&buf[1]), kChunk, cudaHostAllocDefault) == cudaSuccess &&
+		     cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) == cudaSuccess &&
+		     cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+		if (!ok) cudaGetLastError();
+		threads = std::max(1, std::min(16, (int)std::thread::hardware_concurrency()));
 	}
-	~Arena() { for (void* q : ptrs) if (q) cudaFree(q); }
+	~Bounce() {
+		for (char* b : buf) if (b) cudaFreeHost(b);
+		for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+		if (st) cudaStreamDestroy(st);
+	}
+	void host_copy(char* dst, const char* src, size_t n) const {  // own threads, not OpenMP (a second runtime may live in the process)
+		const int T = n < (4u << 20) ? 1 : threads;
+		std::vector<std::thread> th;
+		for (int t = 1; t < T; t++) th.emplace_back([=] { std::memcpy(dst + n * t / T, src + n * t / T, n * (t + 1) / T - n * t / T); });
+		std::memcpy(dst, src, n / T);
+		for (auto& x : th) x.join();
+	}
+	// both wait for everything queued on the legacy stream first (the data they move was produced / is consumed there)
+	int h2d(void* dst, const void* src, size_t bytes) {
+		if (!ok) { CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return BL_OK; }
+		CU(cudaStreamSynchronize(0));
+		for (size_t o = 0, i = 0; o < bytes; o += kChunk, i++) {
+			const size_t n = std::min(kChunk, bytes - o);
+			if (i >= 2) CU(cudaEventSynchronize(ev[i & 1]));
+			host_copy(buf[i & 1], static_cast<const char*>(src) + o, n);
+			CU(cudaMemcpyAsync(static_cast<char*>(dst) + o, buf[i & 1], n, cudaMemcpyHostToDevice, st));
+			CU(cudaEventRecord(ev[i & 1], st));
+		}
+		CU(cudaStreamSynchronize(st));
+		return BL_OK;
+	}
+	int d2h(void* dst, const void* src, size_t bytes) {
+		if (!ok) { CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return BL_OK; }
+		CU(cudaStreamSynchronize(0));
+		const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+		for (size_t i = 0; i <= n_chunks; i++) {
+			if (i < n_chunks) {  // chunk i on its way while chunk i - 1 is copied out of its buffer below
+				const size_t o = i * kChunk;
+				CU(cudaMemcpyAsync(buf[i & 1], static_cast<const char*>(src) + o, std::min(kChunk, bytes - o), cudaMemcpyDeviceToHost, st));
+				CU(cudaEventRecord(ev[i & 1], st));
+			}
+			if (i > 0) {
+				const size_t o = (i - 1) * kChunk;
+				CU(cudaEventSynchronize(ev[(i - 1) & 1]));
+				host_copy(static_cast<char*>(dst) + o, buf[(i - 1) & 1], std::min(kChunk, bytes - o));
+			}
+		}
+		return BL_OK;
+	}
 };
 
 // ---- exclusive scan: out[i] = sum of in[0, i), block sums in bsum ----------------------------------------------------
@@ -568,6 +642,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	};
 	mark("start");
 	Arena A;
+	Bounce X;
 	Scan S;
 	cudaEvent_t ev0, ev1;
 	CU(cudaEventCreate(&ev0));
@@ -576,6 +651,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	CU(cudaEventRecord(ev0, 0));
 
 	char* d_text; uint64_t *d_starts, *d_vstart; uint8_t *d_codes, *d_rem, *d_flag; uint32_t *d_key, *d_kmin, *d_err; uint64_t* d_skidx;
+	A.hint(text_len + n_views * 16 + total_v * 19 + (total_v / kTile + 2) * 10 + 4096);
 #define AL(p, n, ...) do { rc = A.alloc(&p, n, ##__VA_ARGS__); if (rc != BL_OK) { set_err(g_last_error); return rc; } } while (0)
 	AL(d_text, text_len + 64);
 	AL(d_starts, n_views);
@@ -587,7 +663,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	AL(d_flag, total_v);
 	AL(d_skidx, total_v);
 	AL(d_err, 1, true);
-	CU(cudaMemcpy(d_text, text, text_len, cudaMemcpyHostToDevice));
+	if ((rc = X.h2d(d_text, text, text_len)) != BL_OK) { set_err(g_last_error); return rc; }
 	CU(cudaMemcpy(d_starts, starts.data(), n_views * 8, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(d_vstart, vstart.data(), (n_views + 1) * 8, cudaMemcpyHostToDevice));
 	CU(cudaMemset(d_key, 0xFF, (total_v + 64) * 4));
@@ -612,6 +688,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	H.number_super_kmer = n_sk;
 
 	uint64_t* d_sk_v; uint32_t *d_sk_mini, *d_sk_nk; unsigned long long *d_bnuc, *d_bkm;
+	A.hint(n_sk * 56 + H.n_buckets * 24 + ((n_sk + kRadixTile - 1) / kRadixTile) * 256 * 13 + H.n_mphf * (sizeof(GroupDev) + 16) + 65536);
 	AL(d_sk_v, n_sk);
 	AL(d_sk_mini, n_sk);
 	AL(d_sk_nk, n_sk);
@@ -722,6 +799,7 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	mark("group descriptors (host)");
 	// 3. bucket sequences
 	uint64_t* d_seq;
+	A.hint(H.seq_words * 8 + N * 40 + total_bits / 4 + H.pos_words * 8 + total_blocks * 20 + H.n_mphf * 8 + 65536);
 	AL(d_seq, H.seq_words + 1);
 	if (H.seq_words) {
 		k_seq_words<<<grid_for(H.seq_words), kT>>>(d_dest, n_sk, d_perm, d_sk_v, d_codes, H.total_nuc, H.seq_words, d_seq);
@@ -753,7 +831,8 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	for (int level = 0; level < kLevels && n_items; level++) {
 		const unsigned gi = grid_for(n_items, kT * 2);
 		k_level_place<<<gi, kT>>>(d_keys, d_kgroup, list, n_items, level, d_groups, d_bits, d_coll, d_gcoll);
-		if (!d_la) { AL(d_la, n_items); AL(d_lb, n_items); }  // the first sift keeps at most every key
+		if (!d_la) AL(d_la, n_items);  // the first sift keeps at most every key
+		if (list == d_la && !d_lb) AL(d_lb, n_items);  // survivors of level 1: at most what level 0 left
 		uint64_t* next = (list == d_la) ? d_lb : d_la;
 		CU(cudaMemset(d_nnext, 0, 8));
 		k_level_sift<<<gi, kT>>>(d_keys, d_kgroup, list, n_items, level, d_groups, d_coll, next, d_nnext, d_final);
@@ -803,9 +882,9 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 	F.bits.assign(total_bits / 64, 0);
 	std::vector<uint64_t> ranks_all(total_blocks), blockpop_last;
 	std::vector<uint32_t> flevel(H.n_mphf);
-	if (H.seq_words) CU(cudaMemcpy(F.seq.data(), d_seq, H.seq_words * 8, cudaMemcpyDeviceToHost));
-	CU(cudaMemcpy(F.pos.data(), d_pos, H.pos_words * 8, cudaMemcpyDeviceToHost));
-	if (total_bits) CU(cudaMemcpy(F.bits.data(), d_bits, total_bits / 8, cudaMemcpyDeviceToHost));
+	if (H.seq_words && (rc = X.d2h(F.seq.data(), d_seq, H.seq_words * 8)) != BL_OK) { set_err(g_last_error); return rc; }
+	if ((rc = X.d2h(F.pos.data(), d_pos, H.pos_words * 8)) != BL_OK) { set_err(g_last_error); return rc; }
+	if (total_bits && (rc = X.d2h(F.bits.data(), d_bits, total_bits / 8)) != BL_OK) { set_err(g_last_error); return rc; }
 	if (total_blocks) CU(cudaMemcpy(ranks_all.data(), d_ranks, total_blocks * 8, cudaMemcpyDeviceToHost));
 	CU(cudaMemcpy(flevel.data(), d_flevel, H.n_mphf * 4, cudaMemcpyDeviceToHost));
 	if (seconds_device) { float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); *seconds_device = ms * 1e-3; }

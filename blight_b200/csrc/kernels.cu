@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
 	__shared__ uint64_t s_run_T[kWarps][kMaxRuns];   // where the run's first k-mer matched (absolute base position)
 	__shared__ uint64_t s_run_o[kSlot ? kWarps : 1][kMaxRuns];  // output slot of the run's first k-mer
 	__shared__ uint32_t s_run_mn[kWarps][kMaxRuns];  // minimizer of the run
+	__shared__ uint32_t s_run_key[kWarps][kMaxRuns]; // its ordering key, as the front end found it
 	__shared__ uint16_t s_run_q[kWarps][kMaxRuns];   // strip position of the run's first k-mer
 	__shared__ uint16_t s_run_dmax[kWarps][kMaxRuns];// largest distance whose predicted window still starts inside the bucket
 	__shared__ uint8_t s_run_flag[kWarps][kMaxRuns]; // bit0: first k-mer found, bit1: text and read on the same strand
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
 	uint32_t* keys = s_keys[wid];
 	uint8_t* runid = reinterpret_cast<uint8_t*>(s_runid8[wid]);
 	const uint32_t ow = kSlot ? wid : 0;
-	const StripSmem S{pack, s_bad[wid], keys, s_run_q[wid], s_run_o[ow], s_runid8[wid]};
+	const StripSmem S{pack, s_bad[wid], keys, s_run_q[wid], s_run_key[wid], s_run_o[ow], s_runid8[wid]};
 	const uint32_t w = k - m + 1;
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
 	const uint32_t lt_mask = (1u << lane) - 1u;
@@ -473,9 +474,11 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
 					uint64_t o = 0;
 					if (phase == 1 && id != kTagOverflow) {
 						mn = s_run_mn[wid][id];
+					} else if (phase == 0) {
+						mn = mini_from_key(s_run_key[wid][id]);
+						s_run_mn[wid][id] = mn;
 					} else {
 						mn = mini_from_key(window_min_slow(keys, q, w));
-						if (phase == 0) s_run_mn[wid][id] = mn;
 					}
 					if (kSlot) {
 						if (id != kTagOverflow) {

@@ -85,12 +85,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 	__shared__ uint32_t s_keys[kWarps][kKeySlots];
 	__shared__ uint64_t s_run_o[WANT_O ? kWarps : 1][kMaxRuns];
 	__shared__ uint16_t s_run_q[kWarps][kMaxRuns];
+	__shared__ uint32_t s_run_key[kWarps][kMaxRuns];
 	__shared__ uint32_t s_run_n[kWarps][kMaxRuns];  // k-mers of the run inside this strip
 	__shared__ uint64_t s_runid8[kWarps][kStrip / 8];
 
 	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t ow = WANT_O ? wid : 0;
-	const StripSmem S{s_pack[wid], s_bad[wid], s_keys[wid], s_run_q[wid], s_run_o[ow], s_runid8[wid]};
+	const StripSmem S{s_pack[wid], s_bad[wid], s_keys[wid], s_run_q[wid], s_run_key[wid], s_run_o[ow], s_runid8[wid]};
 	const uint8_t* runid = reinterpret_cast<const uint8_t*>(s_runid8[wid]);
 	const uint32_t w = k - m + 1;
 	const uint32_t nmax = min(64u - k + 1u, kMaxRecKmers);  // k-mers one record carries (64 bases)
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 			}
 			uint32_t mn = 0, dst = 0;
 			if (n) {
-				mn = mini_from_key(window_min_slow(S.keys, q, w));
+				mn = mini_from_key(i < n_tab ? s_run_key[wid][i] : window_min_slow(S.keys, q, w));
 				dst = owner_of(R, mn);
 			}
 			#pragma unroll 1
