@@ -65,7 +65,6 @@ def parse():
     ap.add_argument("--partition-genome", type=int, default=1_000_000_000)
     ap.add_argument("--partition-reads", type=int, default=4_000_000, help="reads per GPU per batch of the partitioned leg")
     ap.add_argument("--partition-shape", default="9,10,6", help="m,n,b of the partitioned index")
-    ap.add_argument("--partition-sub", type=int, default=128 << 20, help="base positions per sub-batch of the partitioned leg")
     ap.add_argument("--build-blob", default=None, help=argparse.SUPPRESS)  # internal: build the workload index, save it, exit
     return ap.parse_args()
 
@@ -399,28 +398,37 @@ def partition_leg(args, rank, world, local, dev):
 
     del scratch
     variants, same_all, ctr_ok_all, ovf_all = {}, True, True, False
-    sub_d = args.partition_sub
-    for name, order, ret, sub in ((f"serial/stream/{sub_d >> 20}M", "serial", "stream", sub_d), ("serial/stream/32M", "serial", "stream", 32 << 20),
-                                  ("serial/stream/256M", "serial", "stream", 256 << 20), (f"ahead/stream/{sub_d >> 20}M", "ahead", "stream", sub_d),
-                                  (f"serial/direct/{sub_d >> 20}M", "serial", "direct", sub_d)):
-        if name in variants:
-            continue
-        part.enable_fused(sub_positions=sub, ids_capacity=total, order=order, return_path=ret)
-        ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
-        torch.cuda.synchronize()
-        same = torch.tensor([1 if torch.equal(ids_f, ids_one) else 0], device=dev)
-        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    def measure(sub, want_ids_session):
+        part.enable_fused(want_ids=want_ids_session, sub_positions=sub, ids_capacity=total if want_ids_session else 0)
+        out = {"sub_positions": part._sub}
+        ok_ids = ok_ctr = True
+        if want_ids_session:
+            ids_f, ctr_f = part.query_reads_fused(bases, roff, koff, total)
+            torch.cuda.synchronize()
+            same = torch.tensor([1 if torch.equal(ids_f, ids_one) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            ok_ids = bool(same.item())
+            ok_ctr = bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]))
+            out["ids_ms"] = timed(lambda: part.query_reads_fused(bases, roff, koff, total, check_overflow=False))
+            out["ids_vs_one_gpu"] = world * one_ids_ms / out["ids_ms"]
         _, ctr_c = part.query_reads_fused(bases, roff, want_ids=False)
         torch.cuda.synchronize()
-        ctr_ok = bool(torch.equal(ctr_f.cpu()[:3], ctr_all.cpu()[:3]) and torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
-        f_ids_ms = timed(lambda: part.query_reads_fused(bases, roff, koff, total, check_overflow=False))
-        f_cnt_ms = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False))
+        ok_ctr = ok_ctr and bool(torch.equal(ctr_c.cpu()[:3], ctr_all.cpu()[:3]))
+        out["counting_ms"] = timed(lambda: part.query_reads_fused(bases, roff, want_ids=False, check_overflow=False))
+        out["counting_vs_one_gpu"] = world * one_cnt_ms / out["counting_ms"]
         ovf = torch.tensor([1 if part.overflowed() else 0], device=dev)
         dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
-        variants[name] = {"ids_ms": f_ids_ms, "counting_ms": f_cnt_ms, "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms,
-                           "counting_vs_one_gpu": world * one_cnt_ms / f_cnt_ms, "ids_equal_replica": bool(same.item()),
-                           "counters_equal_replica": ctr_ok, "overflow": bool(ovf.item())}
-        same_all &= bool(same.item()); ctr_ok_all &= ctr_ok; ovf_all |= bool(ovf.item())
+        out.update({"ids_equal_replica": ok_ids, "counters_equal_replica": ok_ctr, "overflow": bool(ovf.item())})
+        return out
+
+    variants, same_all, ctr_ok_all, ovf_all = {}, True, True, False
+    for sub in sorted({32 << 20, bdist.DEFAULT_SUB_IDS, 128 << 20, bdist.DEFAULT_SUB_COUNTING}):
+        v = measure(sub, True)
+        variants[f"{sub >> 20}M"] = v
+        same_all &= v["ids_equal_replica"]; ctr_ok_all &= v["counters_equal_replica"]; ovf_all |= v["overflow"]
+    f_ids_ms = variants[f"{bdist.DEFAULT_SUB_IDS >> 20}M"]["ids_ms"]
+    f_cnt_ms = variants[f"{bdist.DEFAULT_SUB_COUNTING >> 20}M"]["counting_ms"]
+    default_order = f"ids: sub-batches of {bdist.DEFAULT_SUB_IDS >> 20} M positions; counting: {bdist.DEFAULT_SUB_COUNTING >> 20} M (the library's defaults per mode, blight_b200/dist.py)"
     del ids_one, whole
     torch.cuda.empty_cache()
     default_order = f"serial/stream/{sub_d >> 20}M"
@@ -440,8 +448,8 @@ def partition_leg(args, rank, world, local, dev):
                                 "ids_ms": one_ids_ms, "counting_ms": one_cnt_ms, "device_bytes": whole_bytes},
         "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms, "counting_vs_one_gpu": world * one_cnt_ms / f_cnt_ms,
         "ids_equal_replica": same_all, "counters_equal_replica": ctr_ok_all, "overflow": ovf_all,
-        "variant": default_order, "variants": variants,
-        "device_bytes_per_gpu": local_bytes, "cuts": part.plan.cuts, "sub_positions": part._sub,
+        "variant": default_order, "by_sub_batch_size": variants,
+        "device_bytes_per_gpu": local_bytes, "cuts": part.plan.cuts,
         "return_path": "stream: an owner's warp stores its 32-bit ids as one contiguous run into the source's return region, the source widens them into read order one sub-batch behind; ordering between GPUs by device-side flags (csrc/part_session.cu)",
         "build_seconds": build_s, "leg_seconds": time.time() - t_leg,
     }

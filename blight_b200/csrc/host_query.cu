@@ -122,6 +122,7 @@ private:
 
 struct HostCtx {
 	std::unique_ptr<PackPool> pool;
+	int pack_skip = 0;  // calls left without the packer (it did not pay last time it ran, see host_query_records)
 	cudaStream_t st_f = nullptr, st_b = nullptr, cs_raw = nullptr, cs_pk = nullptr;
 	cudaEvent_t ev_f[2] = {nullptr, nullptr}, ev_slot[kSlots] = {nullptr, nullptr, nullptr}, ev_join = nullptr;
 	uint32_t* stage[kSlots] = {nullptr, nullptr, nullptr};
@@ -347,7 +348,8 @@ int host_query_records(const blight_index* idx, const char* text, uint64_t len, 
 		if (kb) chunk = ((kb << 10) + kReadsStrip - 1) / kReadsStrip * kReadsStrip;
 	}
 	const int threads = pack_threads();
-	const bool pack = allow_pack && pack_enabled() && len >= 4 * chunk;
+	bool pack = allow_pack && pack_enabled() && len >= 4 * chunk;
+	if (pack && C.pack_skip > 0) { C.pack_skip--; pack = false; }
 
 	Plan P{};
 	P.idx = idx; P.C = &C; P.text = text; P.len = len; P.beg = beg; P.end = end; P.koff = koff; P.n = n;
@@ -394,6 +396,16 @@ int host_query_records(const blight_index* idx, const char* text, uint64_t len, 
 	}
 	rc = front_producer(P);
 	if (back.joinable()) back.join();
+	if (pack && P.sf.chunks && P.sb.chunks) {
+		// Did the packer pay? It spends host memory bandwidth (every base is read by a core AND its packed form by the DMA
+		// engine) to save link bandwidth. Where the host side is what limits the box — 8 GPUs pulling from one memory system —
+		// its chunks arrive slower than plain copies would: then leave it out for a while (measured on the 8-GPU box: 73 ms
+		// per step with it, 67 ms without; on the one-GPU box 30 ms with it, 36 ms without).
+		uint64_t fb = 0, bb = 0;
+		for (int64_t c = 0; c < P.front; c++) fb += P.cut[c + 1] - P.cut[c];
+		for (int64_t c = P.back; c + 1 < (int64_t)P.cut.size(); c++) bb += P.cut[c + 1] - P.cut[c];
+		if (bb * 4 < fb * 3) C.pack_skip = 15;
+	}
 	if (const char* e = getenv("BLIGHT_HOST_DEBUG")) {
 		if (atoi(e))
 			fprintf(stderr, "[blight host] %zu chunks: front %d (sync %.2f ms, enqueue %.2f ms)  back %d (sync %.2f ms, pack %.2f ms, enqueue %.2f ms)  threads %d\n",

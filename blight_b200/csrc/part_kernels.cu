@@ -448,10 +448,22 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 				if (o < lim) __stcs(reinterpret_cast<long long*>(dst + o), v == kIdAbsent ? -1ll : id0 + (long long)v);
 			}
 		} else if (WANT_IDS) {
-			// the warp's answers back to the source: one contiguous stream of 32-bit ids over NVLink
+			// the warp's answers back to the source: one contiguous stream of 32-bit ids over NVLink, 16 bytes per lane and
+			// store (512 bytes per warp instruction) between a scalar head and tail that bring the stream to 16-byte alignment —
+			// remote stores are bound by the number of requests in flight, not by their bytes
 			uint32_t* dst = A.ret[src] + ko0;
-			if ((uint64_t)ko0 + n_ids <= A.kcap)
-				for (uint32_t t = lane; t < n_ids; t += 32) dst[t] = s_ids[iw][t];
+			if ((uint64_t)ko0 + n_ids <= A.kcap) {
+				const uint32_t* sid = s_ids[iw];
+				const uint32_t head = min(n_ids, (4u - (ko0 & 3u)) & 3u);
+				if (lane < head) dst[lane] = sid[lane];
+				const uint32_t n4 = (n_ids - head) >> 2;
+				for (uint32_t g = lane; g < n4; g += 32) {
+					const uint32_t t = head + 4 * g;
+					*reinterpret_cast<uint4*>(dst + t) = make_uint4(sid[t], sid[t + 1], sid[t + 2], sid[t + 3]);
+				}
+				const uint32_t done = head + 4 * n4;
+				if (done + lane < n_ids) dst[done + lane] = sid[done + lane];
+			}
 		}
 	}
 	#pragma unroll

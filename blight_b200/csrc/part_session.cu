@@ -149,6 +149,7 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	s->idx = idx; s->device = idx->device; s->cfg = *cfg;
 	s->region_bytes = cfg->cap * BLIGHT_RUN_RECORD_BYTES;
 	s->kcap = cfg->ret_kmers && cfg->ret_kmers < cfg->sub_positions ? cfg->ret_kmers : cfg->sub_positions;
+	s->kcap = (s->kcap + 255) & ~uint64_t(255);  // region bases stay 16-byte aligned for the vector stores of the return stream
 	s->order = cfg->order;
 	if (s->order == BLIGHT_PART_ORDER_DEFAULT) {
 		s->order = BLIGHT_PART_ORDER_SERIAL;
