@@ -431,8 +431,6 @@ def partition_leg(args, rank, world, local, dev):
     default_order = f"ids: sub-batches of {bdist.DEFAULT_SUB_IDS >> 20} M positions; counting: {bdist.DEFAULT_SUB_COUNTING >> 20} M (the library's defaults per mode, blight_b200/dist.py)"
     del ids_one, whole
     torch.cuda.empty_cache()
-    default_order = f"serial/stream/{sub_d >> 20}M"
-    f_ids_ms, f_cnt_ms = variants[default_order]["ids_ms"], variants[default_order]["counting_ms"]
     local_bytes = part.index.info["device_bytes"]
     part.disable_fused()
     dist.barrier()
@@ -596,7 +594,20 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": world * total_kmers * e_steps / dt, "unit": "k-mers/s",
+        # what the same bytes cost as plain pinned copies on this box, all ranks at once: the floor of e2e once the kernels are
+        # faster than the link (on the 8-GPU box half of the GPUs get 23 GB/s, tools/h2d_bench.py)
+        d_sink = torch.empty(h_bases.numel(), dtype=torch.uint8, device=dev)
+        d_sink.copy_(h_bases, non_blocking=True)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            d_sink.copy_(h_bases, non_blocking=True)
+        torch.cuda.synchronize()
+        ht = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ht, op=dist.ReduceOp.MAX)
+        del d_sink
+        e2e = {"value": world * total_kmers * e_steps / dt, "unit": "k-mers/s", "ascii_copy_only_ms_per_step": 1e3 * float(ht.item()),
                "h2d_bytes_per_step": (x1[0] - x0[0]) // e_steps, "d2h_bytes_per_step": (x1[1] - x0[1]) // e_steps,
                "ascii_bytes_per_step": int(h_bases.numel()), "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps,
                "mode": "bool (file_query counters), pinned host reads; part of the batch crosses PCIe 2-bit packed by the host cores (bytes as counted by the library)",

@@ -305,3 +305,38 @@ def test_large_scale_properties(torch_cuda):
     c = idx.query_kmers(canon.contiguous(), mini=mini.contiguous())
     torch.cuda.synchronize()
     assert torch.equal(a, c)
+
+
+def test_packed_reads_on_the_device(tmp_path, torch_cuda):
+    """Reads held as 2-bit codes (blight_query_reads_packed: 16 bases per word, first base in the high bits, nuc2int's codes):
+    same ids and counters as the ASCII entry point and the oracle, ragged lengths included; and the host packer's output
+    (what blight_query_reads_host sends for its packed chunks) is that very layout."""
+    torch = torch_cuda
+    rng = np.random.default_rng(11)
+    g, ub, uo, _, _ = common.synthetic(500_000, 10, seed=21)
+    flat = api.FlatIndex.build_seqs(ub, uo, k=31, m=9, n=6, s=0, b=5, threads=0)
+    port = common.cport_of(flat, tmp_path)
+    idx = flat.upload(0)
+    lens = np.concatenate([rng.integers(1, 80, 300), rng.integers(100, 3000, 400), [31, 30, 32, 2048, 4096 + 30]])
+    rng.shuffle(lens)
+    starts = rng.integers(0, len(g) - 5001, len(lens))
+    rb = np.concatenate([g[s:s + l] for s, l in zip(starts, lens)])
+    sub = rng.random(len(rb)) < 0.02
+    rb = np.where(sub, synth.ACGT[rng.integers(0, 4, len(rb))], rb).astype(np.uint8)
+    ro = np.zeros(len(lens) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=ro[1:])
+    want, wctr = port.query_reads(rb, ro)
+    code = ((rb >> 1) & 3).astype(np.uint64)
+    pad = (-len(code)) % 16
+    code = np.concatenate([code, np.zeros(pad + 64, dtype=np.uint64)])
+    sh = np.arange(30, -2, -2, dtype=np.uint64)
+    packed = (code.reshape(-1, 16) << sh).sum(1).astype(np.uint32)
+    d_p = torch.from_numpy(packed.view(np.int32)).cuda()
+    d_o = torch.from_numpy(ro.astype(np.int64)).cuda()
+    koff = synth.kmer_offsets(ro, 31)
+    d_k = torch.from_numpy(koff.astype(np.int64)).cuda()
+    ids, ctr = idx.query_reads_packed(d_p, d_o, len(rb), d_k, int(koff[-1]))
+    _, ctr2 = idx.query_reads_packed(d_p, d_o, len(rb), want_ids=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(ids.cpu().numpy()[:int(koff[-1])], want)
+    assert [int(c) for c in ctr.cpu()[:3]] == [int(c) for c in wctr[:3]] == [int(c) for c in ctr2.cpu()[:3]]
