@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--packed-input", action="store_true", help="diagnostic: the reads are held 2-bit packed on the device (blight_query_reads_packed)")
     ap.add_argument("--compact", action="store_true", help="diagnostic: upload without the derived tables (the reference's arrays only)")
     ap.add_argument("--no-partition", action="store_true", help="N > 1: skip the bucket-partitioned leg")
+    ap.add_argument("--partition-only", action="store_true", help="diagnostic (N > 1): run the bucket-partitioned leg alone and print its record")
+    ap.add_argument("--partition-returns", default="", help="diagnostic: also measure these return paths of the partitioned id mode (comma list of stream,pull,direct)")
     ap.add_argument("--partition-genome", type=int, default=1_000_000_000)
     ap.add_argument("--partition-reads", type=int, default=4_000_000, help="reads per GPU per batch of the partitioned leg")
     ap.add_argument("--partition-shape", default="9,10,6", help="m,n,b of the partitioned index")
@@ -398,8 +400,8 @@ def partition_leg(args, rank, world, local, dev):
 
     del scratch
     variants, same_all, ctr_ok_all, ovf_all = {}, True, True, False
-    def measure(sub, want_ids_session):
-        part.enable_fused(want_ids=want_ids_session, sub_positions=sub, ids_capacity=total if want_ids_session else 0)
+    def measure(sub, want_ids_session, return_path=None):
+        part.enable_fused(want_ids=want_ids_session, sub_positions=sub, ids_capacity=total if want_ids_session else 0, return_path=return_path)
         out = {"sub_positions": part._sub}
         ok_ids = ok_ctr = True
         if want_ids_session:
@@ -426,6 +428,12 @@ def partition_leg(args, rank, world, local, dev):
         v = measure(sub, True)
         variants[f"{sub >> 20}M"] = v
         same_all &= v["ids_equal_replica"]; ctr_ok_all &= v["counters_equal_replica"]; ovf_all |= v["overflow"]
+    other_returns = {}
+    for rp in [x for x in args.partition_returns.split(",") if x]:
+        for sub in (32 << 20, bdist.DEFAULT_SUB_IDS, 128 << 20):
+            v = measure(sub, True, rp)
+            other_returns[f"{rp}/{sub >> 20}M"] = v
+            same_all &= v["ids_equal_replica"]; ctr_ok_all &= v["counters_equal_replica"]; ovf_all |= v["overflow"]
     f_ids_ms = variants[f"{bdist.DEFAULT_SUB_IDS >> 20}M"]["ids_ms"]
     f_cnt_ms = variants[f"{bdist.DEFAULT_SUB_COUNTING >> 20}M"]["counting_ms"]
     default_order = f"ids: sub-batches of {bdist.DEFAULT_SUB_IDS >> 20} M positions; counting: {bdist.DEFAULT_SUB_COUNTING >> 20} M (the library's defaults per mode, blight_b200/dist.py)"
@@ -446,7 +454,7 @@ def partition_leg(args, rank, world, local, dev):
                                 "ids_ms": one_ids_ms, "counting_ms": one_cnt_ms, "device_bytes": whole_bytes},
         "ids_vs_one_gpu": world * one_ids_ms / f_ids_ms, "counting_vs_one_gpu": world * one_cnt_ms / f_cnt_ms,
         "ids_equal_replica": same_all, "counters_equal_replica": ctr_ok_all, "overflow": ovf_all,
-        "variant": default_order, "by_sub_batch_size": variants,
+        "variant": default_order, "by_sub_batch_size": variants, **({"by_return_path": other_returns} if other_returns else {}),
         "device_bytes_per_gpu": local_bytes, "cuts": part.plan.cuts,
         "return_path": "stream: an owner's warp stores its 32-bit ids as one contiguous run into the source's return region, the source widens them into read order one sub-batch behind; ordering between GPUs by device-side flags (csrc/part_session.cu)",
         "build_seconds": build_s, "leg_seconds": time.time() - t_leg,
@@ -480,6 +488,16 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.partition_only:
+        if world < 2:
+            raise SystemExit("--partition-only needs torchrun with at least 2 ranks")
+        pm = partition_leg(args, rank, world, local, dev)
+        if rank == 0:
+            OUT.write(json.dumps(pm) + "\n")
+            OUT.flush()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     tmpdir = tempfile.mkdtemp(prefix="blight_bench_", dir=shm_dir())
     g, flat, blob, build_s = build_workload_index(args, rank, world, tmpdir)
     info = flat.info()

@@ -30,7 +30,7 @@ SYMBOLS = [
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
     "blight_consume_reads", "blight_gather_reads", "blight_fasta_cut_stream", "blight_part_dispatch", "blight_part_lookup", "blight_part_lookup_direct", "blight_part_scatter",
     "blight_part_session_create", "blight_part_session_free", "blight_part_session_handles", "blight_part_session_connect_ipc",
-    "blight_part_session_connect_local", "blight_part_session_ids", "blight_part_session_query", "blight_part_session_status",
+    "blight_part_session_connect_local", "blight_part_session_ids", "blight_part_session_sub_batches", "blight_part_session_query", "blight_part_session_status",
     "blight_comm_init", "blight_comm_free", "blight_comm_describe", "blight_comm_query_reads_host", "blight_comm_query_fasta_host",
     "blight_comm_query_file_host", "blight_comm_query_sequence_host", "blight_peer_alloc", "blight_peer_open", "blight_peer_close", "blight_peer_free",
 ]
@@ -53,7 +53,7 @@ class PartConfig(C.Structure):
 
 
 PART_OVERFLOW, PART_TIMEOUT = 1, 2
-PART_RETURNS = {None: 0, "": 0, "default": 0, "session": 0, "stream": 1, "direct": 2}
+PART_RETURNS = {None: 0, "": 0, "default": 0, "session": 0, "stream": 1, "direct": 2, "pull": 3}
 PART_ORDERS = {None: 0, "": 0, "default": 0, "serial": 1, "ahead": 2, "overlap": 3}
 
 
@@ -169,6 +169,8 @@ def lib() -> C.CDLL:
     L.blight_part_session_ids.argtypes = [vp]
     L.blight_part_session_ids.restype = vp
     L.blight_part_session_query.argtypes = [vp, vp, vp, vp, u64, u64, u64, vp, vp]
+    L.blight_part_session_sub_batches.argtypes = [vp, u64, C.c_int]
+    L.blight_part_session_sub_batches.restype = u64
     L.blight_part_session_status.argtypes = [vp, C.POINTER(u32), C.c_int, vp]
     L.blight_comm_init.argtypes = [vp, C.POINTER(C.c_int), u32, C.c_int, vp, C.POINTER(vp)]
     L.blight_comm_free.argtypes = [vp]
@@ -614,6 +616,10 @@ class PartSession:
         if not p:
             return None
         return torch.as_tensor(_DeviceView(p, self.ids_capacity * 8), device=device).view(torch.int64)
+
+    def sub_batches(self, total_bases: int, want_ids: bool) -> int:
+        """Sub-batches this rank cuts a batch of total_bases positions into (the n_sub of query() is the maximum over the ranks)."""
+        return int(lib().blight_part_session_sub_batches(self._h, int(total_bases), int(bool(want_ids))))
 
     def query(self, bases, read_off, kmer_off, n_sub: int, ctr, stream=None):
         _check(lib().blight_part_session_query(self._h, _ptr(bases), _ptr(read_off), _ptr(kmer_off), read_off.numel() - 1, bases.numel(),

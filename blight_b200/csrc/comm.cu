@@ -147,7 +147,7 @@ int partition_batch(blight_comm* c, const char* text, const uint64_t* beg, const
 		int rc = make_sessions(c, sub, cap, want_ids ? max_kmers + max_kmers / 8 + 1 : c->ids_cap);
 		if (rc != BL_OK) return rc;
 	}
-	const uint64_t n_sub = std::max<uint64_t>(1, (max_len + c->sub - 1) / c->sub);
+	const uint64_t n_sub = std::max<uint64_t>(1, blight_part_session_sub_batches(c->sess[0], max_len, want_ids ? 1 : 0));
 	std::vector<uint64_t> ctrs((size_t)W * BLIGHT_N_CTR, 0);
 	std::vector<uint32_t> flags(W, 0);
 	// Phase 1, every rank: allocations only. cudaMalloc waits for the device to drain (and, with peer access, touches the

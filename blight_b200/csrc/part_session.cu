@@ -24,6 +24,11 @@
 //             region at the source; the source widens them into its int64 id array in read order through a local side table
 //             (k_scatter_runs), one sub-batch behind, on its own stream. S(i) may start once W(i+1) has passed: every owner
 //             published P(i+1) after its L(i).
+//   pull      as stream, but the owner's warp stores its run of ids into its OWN memory (region [half][source]) and the
+//             source's scatter pass fetches them over NVLink with 16-byte loads, all in flight before the first is used.
+//             The lookup kernel then issues no remote store at all: on 8 B200s the pushed streams cost the lookups ~5 ms per
+//             480 M k-mers (remote stores hold the issuing warps' memory pipeline; the loads of the scatter pass stall
+//             nobody but the scatter pass, which runs beside the next sub-batch's lookups).
 //   direct    the owner stores int64 ids straight into the source's id array, run by run. No second pass, but the stores are
 //             ~100-byte segments scattered over a multi-GB array: measured on 8 B200s 160 GB/s per GPU (38.8 ms per batch
 //             of 480 M k-mers) against 17.4 ms for counting — kept for two-GPU boxes, where it is free.
@@ -36,6 +41,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "capi_common.hpp"
 #include "device_index.hpp"
@@ -81,6 +87,18 @@ __global__ void k_wait_counts(const Mailbox* mb, uint32_t world, uint32_t slot, 
 	if (rcv) rcv[s] = mb->count[slot][s];
 }
 
+// Where a batch of `total` base positions is cut into sub-batches: pieces of `full`. (Measured and rejected: pieces that shrink
+// geometrically towards the end of the batch so that less of the last scatter pass is left exposed — 18.27 vs 18.10 ms per
+// 480 M k-mers in loop-back at 192 M positions per sub-batch; the extra barriers cost more than the exposure.)
+std::vector<uint64_t> sub_batch_cuts(uint64_t total, uint64_t full) {
+	std::vector<uint64_t> cuts{0};
+	for (uint64_t at = 0; at < total;) {
+		at += std::min(full, total - at);
+		cuts.push_back(at);
+	}
+	return cuts;
+}
+
 int cu_fail(cudaError_t e, const char* what) { return fail(BL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cu_fail(e__, #call); } while (0)
 
@@ -119,7 +137,8 @@ struct blight_part_session {
 	uint32_t* err = nullptr;
 	unsigned long long seq = 0;  // sub-batches issued so far (same on every rank: the calls are collective)
 	uint32_t order = BLIGHT_PART_ORDER_SERIAL;
-	bool stream_ret = true;
+	bool stream_ret = true;  // 32-bit id streams + scatter pass (stream and pull)
+	bool pull = false;       // ... fetched by the source from the owner's memory instead of pushed by the owner
 	int split_lookup = 2, split_dispatch = 2;  // overlap order: resident CTAs per SM of either kernel while both run
 	cudaStream_t side_st = nullptr;  // overlap order: the lookups' stream
 	cudaStream_t scat_st = nullptr;  // stream return: the scatter pass
@@ -163,10 +182,12 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	uint32_t rp = cfg->return_path;
 	if (rp == BLIGHT_PART_RETURN_DEFAULT) {
 		rp = BLIGHT_PART_RETURN_STREAM;
-		if (const char* e = getenv("BLIGHT_PART_RETURN")) rp = e[0] == 'd' ? BLIGHT_PART_RETURN_DIRECT : BLIGHT_PART_RETURN_STREAM;
+		if (const char* e = getenv("BLIGHT_PART_RETURN"))
+			rp = e[0] == 'd' ? BLIGHT_PART_RETURN_DIRECT : (e[0] == 'p' ? BLIGHT_PART_RETURN_PULL : BLIGHT_PART_RETURN_STREAM);
 	}
-	if (rp != BLIGHT_PART_RETURN_STREAM && rp != BLIGHT_PART_RETURN_DIRECT) { delete s; return fail(BL_ERR_INVALID_ARG, "unknown return path"); }
-	s->stream_ret = rp == BLIGHT_PART_RETURN_STREAM;
+	if (rp != BLIGHT_PART_RETURN_STREAM && rp != BLIGHT_PART_RETURN_DIRECT && rp != BLIGHT_PART_RETURN_PULL) { delete s; return fail(BL_ERR_INVALID_ARG, "unknown return path"); }
+	s->stream_ret = rp != BLIGHT_PART_RETURN_DIRECT;
+	s->pull = rp == BLIGHT_PART_RETURN_PULL;
 	const size_t inbox_bytes = (size_t)2 * cfg->world * s->region_bytes;
 	cudaError_t e = cudaMalloc(&s->inbox, inbox_bytes);
 	if (e == cudaSuccess) e = cudaMemset(s->inbox, 0, inbox_bytes);  // a slot never written must still parse as a (harmless) record
@@ -291,12 +312,18 @@ int blight_part_session_connect_local(blight_part_session* s, uint32_t peer, con
 	s->p_ids_cap[peer] = other->cfg.ids_capacity;
 	s->p_ret[peer] = other->ret;
 	s->id_base[peer] = other->idx->info.id_base;
-	if (other->stream_ret != s->stream_ret) return fail(BL_ERR_INVALID_ARG, "the ranks disagree on the return path");
+	if (other->stream_ret != s->stream_ret || other->pull != s->pull) return fail(BL_ERR_INVALID_ARG, "the ranks disagree on the return path");
 	s->connected |= 1u << peer;
 	return BL_OK;
 }
 
 void* blight_part_session_ids(const blight_part_session* s) { return s ? s->ids : nullptr; }
+
+uint64_t blight_part_session_sub_batches(const blight_part_session* s, uint64_t total_bases, int want_ids) {
+	if (!s) return 0;
+	(void)want_ids;
+	return sub_batch_cuts(total_bases, s->cfg.sub_positions).size() - 1;
+}
 
 int blight_part_session_query(blight_part_session* s, const char* d_bases, const uint64_t* d_read_off, const uint64_t* d_kmer_off,
                               uint64_t n_reads, uint64_t total_bases, uint64_t n_sub, uint64_t* d_ctr, void* stream) {
@@ -317,7 +344,8 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 	if (s->connected != (c.world == 32 ? 0xFFFFFFFFu : ((1u << c.world) - 1u))) return fail(BL_ERR_INVALID_ARG, "not every peer is connected");
 	const bool want_ids = d_kmer_off != nullptr;
 	if (want_ids && !s->ids) return fail(BL_ERR_INVALID_ARG, "the session was created without an id array (ids_capacity)");
-	if (n_sub * c.sub_positions < total_bases) return fail(BL_ERR_INVALID_ARG, "n_sub sub-batches do not cover the reads");
+	const std::vector<uint64_t> sub_cut = sub_batch_cuts(total_bases, c.sub_positions);
+	if (sub_cut.size() - 1 > n_sub) return fail(BL_ERR_INVALID_ARG, "n_sub sub-batches do not cover the reads");
 	Guard g(s->device);
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	const uint32_t world = c.world;
@@ -326,7 +354,8 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 	const bool stream_ret = want_ids && s->stream_ret;
 	blight_part_route routes[2];
 	const void* regions[2][kMaxRanks];
-	void* ret_at[2][kMaxRanks];  // stream return: this owner's region at every source
+	void* ret_at[2][kMaxRanks];          // stream return: where this owner's lookups store the ids of source d (at d; pull: here)
+	const void* ret_from[2][kMaxRanks];  // ... and where this source's scatter pass reads the ids of owner d (here; pull: at d)
 	for (int b = 0; b < 2; b++) {
 		blight_part_route& rt = routes[b];
 		std::memset(&rt, 0, sizeof rt);
@@ -336,13 +365,30 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 		for (uint32_t d = 0; d < world; d++) {
 			rt.inbox[d] = static_cast<char*>(s->p_inbox[d]) + ((size_t)b * world + c.rank) * s->region_bytes;  // [half b][source = me] at owner d
 			regions[b][d] = static_cast<const char*>(s->inbox) + ((size_t)b * world + d) * s->region_bytes;   // [half b][source d] here
-			ret_at[b][d] = stream_ret ? static_cast<void*>(s->p_ret[d] + ((size_t)b * world + c.rank) * s->kcap) : nullptr;  // [half b][owner = me] at source d
+			const size_t mine_at_d = ((size_t)b * world + c.rank) * s->kcap, d_here = ((size_t)b * world + d) * s->kcap;
+			// push: [half b][owner = me] at source d, read back from [half b][owner d] here; pull: [half b][source d] here,
+			// fetched from [half b][source = me] at owner d
+			ret_at[b][d] = stream_ret ? static_cast<void*>(s->pull ? s->ret + d_here : s->p_ret[d] + mine_at_d) : nullptr;
+			ret_from[b][d] = stream_ret ? static_cast<const void*>(s->pull ? s->p_ret[d] + mine_at_d : s->ret + d_here) : nullptr;
 		}
 	}
 	MailPtrs mp{};
 	void* out_ids[kMaxRanks];
 	for (uint32_t d = 0; d < world; d++) { mp.m[d] = s->p_mail[d]; out_ids[d] = s->p_ids[d]; }
 	bool scat_pending[2] = {false, false};
+	// BLIGHT_PART_TRACE=1 (diagnostic): timestamps of every step of the batch, printed per rank when the batch has drained
+	const char* trace_env = getenv("BLIGHT_PART_TRACE");
+	const bool trace_on = trace_env && trace_env[0] == '1';
+	struct Mark { char tag; uint64_t i; cudaEvent_t ev; };
+	std::vector<Mark> marks;
+	auto mark = [&](char tag, uint64_t i, cudaStream_t on) {
+		if (!trace_on) return;
+		cudaEvent_t ev;
+		if (cudaEventCreate(&ev) != cudaSuccess) return;
+		cudaEventRecord(ev, on);
+		marks.push_back({tag, i, ev});
+	};
+	mark('0', 0, st);
 
 	auto dispatch = [&](uint64_t i) -> int {
 		const int b = (int)(i & 1);
@@ -351,12 +397,12 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 			scat_pending[b] = false;
 		}
 		CU(cudaMemsetAsync(s->counts[b], 0, kMaxRanks * 8, st));
-		const uint64_t lo = i * c.sub_positions;
-		if (lo < total_bases && n_reads) {
-			int rc = part_dispatch_batch(s->idx->v.k, s->idx->v.m, RB, lo, std::min<uint64_t>(total_bases, lo + c.sub_positions), &routes[b],
+		if (i + 1 < sub_cut.size() && n_reads) {
+			int rc = part_dispatch_batch(s->idx->v.k, s->idx->v.m, RB, sub_cut[i], sub_cut[i + 1], &routes[b],
 			                             reinterpret_cast<uint64_t*>(s->counts[b]), d_ctr, s->err, st);
 			if (rc != BL_OK) return rc;
 		}
+		mark('D', i, st);
 		return BL_OK;
 	};
 	auto publish = [&](uint64_t i) -> int {
@@ -369,13 +415,16 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 		k_wait_counts<<<1, kMaxRanks, 0, st>>>(s->mail, world, (uint32_t)(i & 1), s->seq + i + 1, s->rcv[i & 1], s->err, spin_limit);
 		g_launches++;
 		CU(cudaGetLastError());
+		mark('W', i, st);
 		return BL_OK;
 	};
 	auto lookup_on = [&](uint64_t i, cudaStream_t on) -> int {
 		const int b = (int)(i & 1);
-		return blight_part_lookup_direct(s->idx, world, regions[b], reinterpret_cast<const uint64_t*>(s->rcv[b]), stream_ret ? ret_at[b] : nullptr,
-		                                 want_ids && !stream_ret ? out_ids : nullptr, want_ids && !stream_ret ? s->p_ids_cap : nullptr, c.cap,
-		                                 s->kcap, d_ctr, on);
+		const int rc = part_lookup_from(s->idx, world, c.rank, regions[b], reinterpret_cast<const uint64_t*>(s->rcv[b]), stream_ret ? ret_at[b] : nullptr,
+		                                         want_ids && !stream_ret ? out_ids : nullptr, want_ids && !stream_ret ? s->p_ids_cap : nullptr, c.cap,
+		                                         s->kcap, d_ctr, on);
+		mark('L', i, on);
+		return rc;
 	};
 	auto lookup = [&](uint64_t i) -> int { return lookup_on(i, st); };
 	// stream return: sub-batch i's ids into the id array, on the scatter stream, once the main stream has passed a point
@@ -385,10 +434,11 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 		const int b = (int)(i & 1);
 		CU(cudaEventRecord(s->ev_pub, st));
 		CU(cudaStreamWaitEvent(s->scat_st, s->ev_pub, 0));
-		int rc = blight_part_scatter(s->side + (size_t)b * world * c.cap, c.cap, reinterpret_cast<const uint64_t*>(s->counts[b]),
-		                             s->ret + (size_t)b * world * s->kcap, s->kcap, world, (uint64_t)world * c.cap, s->id_base, s->ids,
-		                             s->scat_st);
+		mark('s', i, s->scat_st);
+		int rc = part_scatter_from(s->side + (size_t)b * world * c.cap, c.cap, reinterpret_cast<const uint64_t*>(s->counts[b]), ret_from[b], s->kcap,
+		                           world, c.rank, (uint64_t)world * c.cap, s->id_base, s->ids, s->scat_st);
 		if (rc != BL_OK) return rc;
+		mark('S', i, s->scat_st);
 		CU(cudaEventRecord(s->ev_scat[b], s->scat_st));
 		scat_pending[b] = true;
 		return BL_OK;
@@ -440,6 +490,21 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 	for (int b = 0; b < 2; b++)
 		if (scat_pending[b]) CU(cudaStreamWaitEvent(st, s->ev_scat[b], 0));
 #undef STEP
+	if (trace_on) {
+		mark('E', n_sub, st);
+		cudaStreamSynchronize(st);
+		std::string line = "{\"part_trace\": {\"rank\": " + std::to_string(c.rank) + ", \"ids\": " + (want_ids ? "true" : "false") + ", \"t_ms\": [";
+		for (size_t j = 0; j < marks.size(); j++) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, marks[0].ev, marks[j].ev);
+			char buf[64];
+			snprintf(buf, sizeof buf, "%s[\"%c%llu\", %.3f]", j ? ", " : "", marks[j].tag, (unsigned long long)marks[j].i, ms);
+			line += buf;
+		}
+		line += "]}}\n";
+		fputs(line.c_str(), stderr);
+		for (auto& mk : marks) cudaEventDestroy(mk.ev);
+	}
 	return BL_OK;
 }
 

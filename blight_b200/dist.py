@@ -481,7 +481,7 @@ class PartitionedSet:
         if want_ids and not self._fused_ids:
             raise ValueError("enable_fused(want_ids=False) was asked for")
         total = bases.numel()
-        n_sub = (total + self._sub - 1) // self._sub
+        n_sub = self._session.sub_batches(total, want_ids)
         need = int(total_kmers) if want_ids else 0
         if world > 1:
             t = torch.tensor([n_sub, need], dtype=torch.int64, device=dev)

@@ -262,9 +262,10 @@ typedef struct blight_part_config {
 	uint64_t ret_kmers;                  /* stream return: ids per (owner, sub-batch) region; 0 = sub_positions (can never overflow);
 	                                        smaller saves memory, a sub-batch sending one owner more raises BLIGHT_PART_OVERFLOW */
 } blight_part_config;
-#define BLIGHT_PART_RETURN_DEFAULT 0u /* what BLIGHT_PART_RETURN says (stream | direct), else stream */
+#define BLIGHT_PART_RETURN_DEFAULT 0u /* what BLIGHT_PART_RETURN says (stream | pull | direct), else the library's choice */
 #define BLIGHT_PART_RETURN_STREAM 1u  /* contiguous 32-bit id streams per owner warp + a scatter pass at the source */
 #define BLIGHT_PART_RETURN_DIRECT 2u  /* int64 ids stored by the owner straight into the source's id array */
+#define BLIGHT_PART_RETURN_PULL 3u    /* as STREAM, but the streams stay in the owner's memory and the source's scatter pass fetches them */
 #define BLIGHT_PART_ORDER_DEFAULT 0u /* what BLIGHT_PART_ORDER says (serial | ahead | overlap), else the library's choice */
 #define BLIGHT_PART_ORDER_SERIAL 1u  /* dispatch(i), lookup(i), dispatch(i+1), ... on one stream */
 #define BLIGHT_PART_ORDER_AHEAD 2u   /* dispatch(i+1) before lookup(i) on one stream: the wait for the peers never sees dispatch skew */
@@ -282,6 +283,9 @@ int blight_part_session_connect_local(blight_part_session* s, uint32_t peer, con
 /* DEVICE pointer of this rank's id array: after a query (and a synchronisation of its stream) slot d_kmer_off[r] + pos holds
  * the identifier query_sequence_hash would return for k-mer pos of read r (blight.cpp:575-591). */
 void* blight_part_session_ids(const blight_part_session* s);
+/* Sub-batches this rank cuts a batch of total_bases base positions into: ceil(total_bases / sub_positions). The n_sub of a
+ * query is the maximum of this over the ranks. */
+uint64_t blight_part_session_sub_batches(const blight_part_session* s, uint64_t total_bases, int want_ids);
 /* One batch of reads held by THIS rank, collective: every rank calls it with the same n_sub (>= ceil(total_bases /
  * sub_positions) of every rank) and the same mode (d_kmer_off NULL everywhere = counting). Asynchronous on `stream`.
  * d_ctr accumulates QUERIES / INVALID for this rank's reads and FOUND / NOT_FOUND for the k-mers this rank OWNS: sum the

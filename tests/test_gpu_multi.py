@@ -18,7 +18,7 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("ret", ["stream", "stream+ahead", "stream+overlap", "direct", "legacy"])
+@pytest.mark.parametrize("ret", ["stream", "pull", "stream+ahead", "pull+overlap", "direct", "legacy"])
 def test_partition_ids_equal_replica_on_real_peers(ret):
     n = _n_gpus()
     if n < 2:

@@ -26,11 +26,12 @@ def _dev_batch(torch, rb, ro, k=31):
             torch.from_numpy(koff.astype(np.int64)).cuda(), int(koff[-1]))
 
 
-@pytest.mark.parametrize("mode", ["stream", "direct", "legacy"])
+@pytest.mark.parametrize("mode", ["stream", "pull", "direct", "legacy"])
 @pytest.mark.parametrize("shape", [(9, 6, 6), (7, 5, 0), (11, 8, 8)])
 def test_loopback_partition_matches_oracle(shape, mode, tmp_path, torch_cuda, monkeypatch):
-    """stream / direct: the session of part_session.cu (ordering by device-side flags) with its two return paths — 32-bit id
-    streams + scatter pass at the source, or int64 ids stored by the owner straight into the source's id array;
+    """stream / pull / direct: the session of part_session.cu (ordering by device-side flags) with its return paths — 32-bit id
+    streams pushed into the source's return region or left in the owner's memory for the source to fetch, + scatter pass at
+    the source; or int64 ids stored by the owner straight into the source's id array;
     legacy: round 1's Python pipeline (a counter all-to-all per sub-batch)."""
     torch = torch_cuda
     if mode == "legacy":
@@ -175,7 +176,8 @@ def test_three_sessions_on_one_gpu(tmp_path, torch_cuda):
     owners = [flat.slice(*plan.group_range(r)).upload(0) for r in range(world)]
     koff_all = synth.kmer_offsets(ro, 31)
     cutsr = [0, 6000, 9000, 9000]  # reads per rank: 6000, 3000, 0
-    for order, ret in (("serial", "stream"), ("ahead", "stream"), ("overlap", "stream"), ("serial", "direct"), ("overlap", "direct")):
+    for order, ret in (("serial", "stream"), ("ahead", "stream"), ("overlap", "stream"), ("serial", "pull"), ("ahead", "pull"), ("overlap", "pull"),
+                       ("serial", "direct"), ("overlap", "direct")):
         sub = 1 << 17
         sess, batches = [], []
         for r in range(world):

@@ -52,16 +52,21 @@ one_cnt = timed(lambda: ps.index.query_reads(bases, roff, want_ids=False))
 del scratch
 print(json.dumps({"variant": "one kernel (k_reads_sk)", "ids_ms": one_ids, "counting_ms": one_cnt}), flush=True)
 variants = []
-for sub in (32 << 20, 64 << 20, 128 << 20, 256 << 20):
+if os.environ.get("TUNE_SUBS"):
+    variants = [(int(x) << 20, "serial", None, "stream") for x in os.environ["TUNE_SUBS"].split(",")]
+for sub in (() if os.environ.get("TUNE_SUBS") else (32 << 20, 64 << 20, 128 << 20, 256 << 20)):
     variants.append((sub, "serial", None, "stream"))
-variants += [(64 << 20, "ahead", None, "stream"), (64 << 20, "serial", None, "direct")]
-for split in ("2,2", "3,1", "3,2", "2,1", "4,1"):
-    variants.append((64 << 20, "overlap", split, "stream"))
-variants.append((128 << 20, "overlap", "3,1", "stream"))
+if not os.environ.get("TUNE_SUBS"):
+    variants += [(64 << 20, "ahead", None, "stream"), (64 << 20, "serial", None, "direct"), (64 << 20, "serial", None, "pull"), (32 << 20, "serial", None, "pull")]
+if os.environ.get("TUNE_OVERLAP"):
+    for split in ("2,2", "3,1", "3,2", "2,1", "4,1"):
+        variants.append((64 << 20, "overlap", split, "stream"))
+    variants.append((128 << 20, "overlap", "3,1", "stream"))
 for sub, order, split, ret in variants:
     if split:
         os.environ["BLIGHT_PART_SPLIT"] = split
-    ps.enable_fused(sub_positions=sub, ids_capacity=total, order=order, return_path=ret)
+    ps.enable_fused(sub_positions=sub, ids_capacity=total, order=order, return_path=ret,
+                    records_per_position=float(os.environ["TUNE_RPP"]) if os.environ.get("TUNE_RPP") else None)
     ids, _ = ps.query_reads_fused(bases, roff, koff, total)
     torch.cuda.synchronize()
     ok = bool(torch.equal(ids, want))
