@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--compact", action="store_true", help="diagnostic: upload without the derived tables (the reference's arrays only)")
     ap.add_argument("--no-partition", action="store_true", help="N > 1: skip the bucket-partitioned leg")
     ap.add_argument("--partition-only", action="store_true", help="diagnostic (N > 1): run the bucket-partitioned leg alone and print its record")
-    ap.add_argument("--partition-returns", default="", help="diagnostic: also measure these return paths of the partitioned id mode (comma list of stream,pull,direct)")
+    ap.add_argument("--partition-returns", default="stream", help="also measure these return paths of the partitioned id mode at the default sub-batch size (comma list of stream,pull,direct; the library's default is direct)")
     ap.add_argument("--partition-genome", type=int, default=1_000_000_000)
     ap.add_argument("--partition-reads", type=int, default=4_000_000, help="reads per GPU per batch of the partitioned leg")
     ap.add_argument("--partition-shape", default="9,10,6", help="m,n,b of the partitioned index")
@@ -424,13 +424,13 @@ def partition_leg(args, rank, world, local, dev):
         return out
 
     variants, same_all, ctr_ok_all, ovf_all = {}, True, True, False
-    for sub in sorted({32 << 20, bdist.DEFAULT_SUB_IDS, 128 << 20, bdist.DEFAULT_SUB_COUNTING}):
+    for sub in sorted({64 << 20, bdist.DEFAULT_SUB_IDS, bdist.DEFAULT_SUB_COUNTING}):
         v = measure(sub, True)
         variants[f"{sub >> 20}M"] = v
         same_all &= v["ids_equal_replica"]; ctr_ok_all &= v["counters_equal_replica"]; ovf_all |= v["overflow"]
     other_returns = {}
     for rp in [x for x in args.partition_returns.split(",") if x]:
-        for sub in (32 << 20, bdist.DEFAULT_SUB_IDS, 128 << 20):
+        for sub in (bdist.DEFAULT_SUB_IDS,):
             v = measure(sub, True, rp)
             other_returns[f"{rp}/{sub >> 20}M"] = v
             same_all &= v["ids_equal_replica"]; ctr_ok_all &= v["counters_equal_replica"]; ovf_all |= v["overflow"]
@@ -456,7 +456,7 @@ def partition_leg(args, rank, world, local, dev):
         "ids_equal_replica": same_all, "counters_equal_replica": ctr_ok_all, "overflow": ovf_all,
         "variant": default_order, "by_sub_batch_size": variants, **({"by_return_path": other_returns} if other_returns else {}),
         "device_bytes_per_gpu": local_bytes, "cuts": part.plan.cuts,
-        "return_path": "stream: an owner's warp stores its 32-bit ids as one contiguous run into the source's return region, the source widens them into read order one sub-batch behind; ordering between GPUs by device-side flags (csrc/part_session.cu)",
+        "return_path": "direct (the library's default): the owner stores int64 ids straight into the source's id array over NVLink, run by run; owners take their sources round-robin so that no GPU is the target of all the others at once; ordering between GPUs by device-side flags (csrc/part_session.cu). by_return_path: the other return paths at the default sub-batch size",
         "build_seconds": build_s, "leg_seconds": time.time() - t_leg,
     }
 

@@ -316,4 +316,15 @@ __device__ __forceinline__ uint32_t strip_front(const StripSmem& S, uint32_t lan
 }
 
 }  // namespace
+// Next work item of a persistent warp. With a ticket counter (zeroed before the launch) the items past the first one per warp
+// are handed out on demand — a sub-batch is only some 30-50 items per warp and their cost varies (one chunk's lookups walk
+// more BBHash levels than another's), so a fixed stride left the SMs idling behind the slowest warps at every kernel's end.
+__device__ __forceinline__ uint64_t next_item(unsigned long long* ticket, uint64_t cur, uint64_t n_warps, uint64_t first, uint32_t lane) {
+	if (!ticket) return cur + n_warps;
+	unsigned long long t = 0;
+	if (lane == 0) t = atomicAdd(ticket, 1ull);
+	t = __shfl_sync(0xffffffffu, t, 0);
+	return first + n_warps + t;
+}
+
 }  // namespace blight

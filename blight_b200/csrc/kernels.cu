@@ -23,6 +23,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 #include "front.cuh"
 #include "kernels.hpp"
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
                                                     uint64_t strip_lo, uint64_t strip_hi, bool aligned16, const uint32_t* __restrict__ packed,
                                                     double reads_per_base, uint64_t guess_p0, uint64_t* __restrict__ out_canon,
                                                     uint32_t* __restrict__ out_mini, int64_t* __restrict__ out_ids,
-                                                    uint64_t* __restrict__ ctr) {
+                                                    uint64_t* __restrict__ ctr, unsigned long long* ticket) {
 	__shared__ uint32_t s_pack[kWarps][kStripWords];  // 2-bit codes, 16 per word, first base in the high bits
 	__shared__ uint32_t s_bad[kWarps][kStripWords];   // 1 bit per base (bit 15-j of word i = base 16i+j): not ACGTacgt
 	__shared__ uint32_t s_keys[kWarps][kStripKeys];   // ordering key of the m-mer starting at each strip position
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_reads(DevIndexView I, uint32_t 
 	const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
 	uint32_t found = 0, notfound = 0, invalid = 0;
 
-	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
+	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip = next_item(ticket, strip, warp_stride, strip_lo, lane)) {
 		const uint64_t t0 = strip * kStrip;
 		const uint32_t n_pos = (uint32_t)min((uint64_t)kStrip, total_bases - t0);                        // positions owned by this strip
 		const uint32_t n_load = (uint32_t)min((uint64_t)(kStrip + 32), total_bases - t0);  // owned + halo (k-1 <= 30)
@@ -319,7 +320,8 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
                                                        const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ read_end,
                                                        const uint64_t* __restrict__ kmer_off, uint64_t n_reads, uint64_t total_bases,
                                                        uint64_t strip_lo, uint64_t strip_hi, bool aligned16, const uint32_t* __restrict__ packed,
-                                                       double reads_per_base, uint64_t guess_p0, Sink K, uint64_t* __restrict__ ctr) {
+                                                       double reads_per_base, uint64_t guess_p0, Sink K, uint64_t* __restrict__ ctr,
+                                                       unsigned long long* ticket) {
 	constexpr bool kSlot = mode_wants_slot<MODE>(), kId = mode_wants_id<MODE>();
 	__shared__ uint32_t s_pack[kWarps][kStripWords];
 	__shared__ uint32_t s_bad[kWarps][kStripWords];
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, BLIGHT_SK_BLOCKS) k_reads_sk(DevInde
 	const bool filter_anchors = I.filter && (I.flags & kFlagFilterAnchors);
 	uint32_t found = 0, notfound = 0, invalid = 0;
 
-	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
+	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip = next_item(ticket, strip, warp_stride, strip_lo, lane)) {
 		const uint64_t t0 = strip * kStrip;
 		__syncwarp();
 		const uint32_t n_runs = strip_front<kSlot>(S, lane, k, m, bases, read_off, read_end, kmer_off, n_reads, total_bases,
@@ -539,6 +541,33 @@ int sm_count() {
 	return sms;
 }
 
+// A zeroed 8-byte device counter for one launch on `stream`: persistent kernels hand their strips out on demand through it
+// (front.cuh: next_item). Slots come from a per-device ring; a slot is reused 4096 launches later, long after its kernel ended.
+// Null (allocation failed, or BLIGHT_TICKETS=0) = fixed stride.
+constexpr int kTicketRing = 4096, kMaxDevices = 64;
+unsigned long long* g_ticket_ring[kMaxDevices] = {};
+std::atomic<uint32_t> g_ticket_next[kMaxDevices];
+std::mutex g_ticket_mu;
+
+unsigned long long* ticket_for_launch(cudaStream_t stream) {
+	static const bool off = [] { const char* e = getenv("BLIGHT_TICKETS"); return e && e[0] == '0'; }();
+	if (off) return nullptr;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+	unsigned long long* ring = g_ticket_ring[dev];
+	if (!ring) {
+		std::lock_guard<std::mutex> lk(g_ticket_mu);
+		ring = g_ticket_ring[dev];
+		if (!ring) {
+			if (cudaMalloc(reinterpret_cast<void**>(&ring), kTicketRing * 8) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+			g_ticket_ring[dev] = ring;
+		}
+	}
+	unsigned long long* slot = ring + (g_ticket_next[dev].fetch_add(1, std::memory_order_relaxed) % kTicketRing);
+	if (cudaMemsetAsync(slot, 0, 8, stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return slot;
+}
+
 template <class K>
 int blocks_per_sm(K kernel) {
 	int nb = 0;
@@ -557,7 +586,8 @@ void launch_reads_plain(const DevIndexView& v, uint32_t k, uint32_t m, const Rea
 	const uint64_t cap = (uint64_t)sm_count() * per_sm;  // persistent: one resident wave, warps stride over the strips
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
 	k_reads<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, B.d_bases, B.d_read_off, B.d_read_end, B.d_kmer_off, B.n_reads, B.total_bases,
-	                                                   strip_lo, strip_hi, al, B.d_packed, rpb_of(B), B.guess_p0, d_canon, d_mini, d_ids, d_ctr);
+	                                                   strip_lo, strip_hi, al, B.d_packed, rpb_of(B), B.guess_p0, d_canon, d_mini, d_ids, d_ctr,
+	                                                   grid == cap ? ticket_for_launch(stream) : nullptr);
 }
 
 // Which read kernel serves a mode. Measured on B200 (100 M-k-mer index, b=6): counting mode 1.88e10 k-mers/s with the
@@ -582,7 +612,8 @@ void launch_reads_sk(const DevIndexView& v, uint32_t k, uint32_t m, const ReadBa
 	const uint64_t cap = (uint64_t)sm_count() * per_sm;
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
 	k_reads_sk<MODE, SMALL><<<grid, kThreads, 0, stream>>>(v, k, m, B.d_bases, B.d_read_off, B.d_read_end, B.d_kmer_off, B.n_reads, B.total_bases,
-	                                                      strip_lo, strip_hi, al, B.d_packed, rpb_of(B), B.guess_p0, sink, d_ctr);
+	                                                      strip_lo, strip_hi, al, B.d_packed, rpb_of(B), B.guess_p0, sink, d_ctr,
+	                                                      grid == cap ? ticket_for_launch(stream) : nullptr);  // fewer CTAs than fit: one strip per warp anyway
 }
 
 template <int MODE, bool SMALL>

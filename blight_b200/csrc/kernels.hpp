@@ -62,7 +62,7 @@ int launch_reads_sink(const DevIndexView& I, int kind, const ReadBatch& B, uint3
 
 // part_kernels.cu: front end + dispatch of the k-mers starting in [pos_begin, pos_end) of a batch (blight_part_dispatch on a ReadBatch)
 int part_dispatch_batch(uint32_t k, uint32_t m, const ReadBatch& B, uint64_t pos_begin, uint64_t pos_end, const ::blight_part_route* route,
-                        uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream);
+                        uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream, uint64_t* d_ticket = nullptr);
 
 // blight_part_scatter with one pointer per owner: ret[d] = where owner d's 32-bit ids for this source are read from (a local
 // region the owner pushed into, or a peer pointer into the owner's own memory: the pull return path of part_session.cu)
@@ -70,7 +70,8 @@ int part_scatter_from(const void* d_side, uint64_t cap, const uint64_t* d_counts
                       uint32_t rank, uint64_t max_records, const uint64_t* id_bases, int64_t* d_ids, void* stream);
 // blight_part_lookup_direct with the owner's rank (where its round-robin over the sources starts)
 int part_lookup_from(const ::blight_index* idx, uint32_t world, uint32_t rank, const void* const* regions, const uint64_t* d_counts,
-                     void* const* ret, void* const* out_ids, const uint64_t* out_caps, uint64_t cap, uint64_t kcap, uint64_t* d_ctr, void* stream);
+                     void* const* ret, void* const* out_ids, const uint64_t* out_caps, uint64_t cap, uint64_t kcap, uint64_t* d_ctr, void* stream,
+                     uint64_t* d_ticket = nullptr);  // d_ticket: zeroed device counter, work handed out on demand (null: fixed stride)
 int part_kernels_preload();
 // resident CTAs per SM the next dispatch / lookup launches of the calling thread may take (0: all that fit)
 extern thread_local int g_part_blocks_per_sm;

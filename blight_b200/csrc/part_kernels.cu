@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
                                                              uint64_t strip_lo, uint64_t strip_hi, bool aligned16, const uint32_t* __restrict__ packed,
                                                              double reads_per_base, uint64_t guess_p0, Route R,
                                                              unsigned long long* __restrict__ counts, uint64_t* __restrict__ ctr,
-                                                             uint32_t* __restrict__ err) {
+                                                             uint32_t* __restrict__ err, unsigned long long* ticket) {
 	__shared__ uint32_t s_pack[kWarps][kStripWords];
 	__shared__ uint32_t s_bad[kWarps][kStripWords];
 	__shared__ uint32_t s_keys[kWarps][kKeySlots];
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dispatch_runs(uint32_t k, uint3
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	uint32_t invalid = 0, queries = 0;
 
-	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip += warp_stride) {
+	for (uint64_t strip = strip_lo + (uint64_t)blockIdx.x * kWarps + wid; strip < strip_hi; strip = next_item(ticket, strip, warp_stride, strip_lo, lane)) {
 		const uint64_t t0 = strip * kStrip;
 		__syncwarp();
 		s_run_n[wid][lane] = 0;
@@ -239,7 +239,7 @@ __device__ __forceinline__ uint32_t run_of(const uint16_t* incl, uint32_t i) {
 
 template <bool WANT_IDS, bool SMALL>
 __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, OwnerArgs A, const unsigned long long* __restrict__ counts,
-                                                           uint64_t* __restrict__ ctr) {
+                                                           uint64_t* __restrict__ ctr, unsigned long long* ticket) {
 	__shared__ unsigned long long s_cnt[kMaxRanks];  // records received from source s
 	__shared__ unsigned long long s_rounds;          // chunks (32 records of one source) of the fullest region
 	__shared__ uint32_t s_w[kWarps][32][kRecWords + 1];  // +1: odd stride
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_runs_lookup(DevIndexView I, Own
 	const uint32_t mn_limit = 1u << (2 * I.m - 1);
 	uint32_t found = 0, notfound = 0;
 
-	for (uint64_t chunk = (uint64_t)blockIdx.x * kWarps + wid; chunk < n_chunks; chunk += warp_stride) {
+	for (uint64_t chunk = (uint64_t)blockIdx.x * kWarps + wid; chunk < n_chunks; chunk = next_item(ticket, chunk, warp_stride, 0, lane)) {
 		const uint64_t round = chunk / A.world;
 		const uint32_t src = (uint32_t)((chunk - round * A.world + A.rank + 1) % A.world);
 		const uint64_t rec0 = round * 32;
@@ -642,7 +642,8 @@ int part_kernels_preload() {
 }
 
 int part_dispatch_batch(uint32_t k, uint32_t m, const ReadBatch& B, uint64_t pos_begin, uint64_t pos_end, const blight_part_route* route,
-                        uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream) {
+                        uint64_t* d_counts, uint64_t* d_ctr, uint32_t* d_err, void* stream, uint64_t* d_ticket) {
+	unsigned long long* tk = reinterpret_cast<unsigned long long*>(d_ticket);
 	const uint64_t n_reads = B.n_reads, total_bases = B.total_bases;
 	if (!route || !d_counts || !d_ctr || !d_err || (n_reads && ((!B.d_bases && !B.d_packed) || !B.d_read_off))) return fail(BL_ERR_INVALID_ARG, "null argument");
 	if (route->world == 0 || route->world > (uint32_t)kMaxRanks || route->rank >= route->world) return fail(BL_ERR_INVALID_ARG, "bad world / rank");
@@ -670,12 +671,12 @@ int part_dispatch_batch(uint32_t k, uint32_t m, const ReadBatch& B, uint64_t pos
 		static const int nb = per_sm(k_dispatch_runs<true>);
 		const uint64_t cap = (uint64_t)sm_count_() * limit_per_sm(nb);
 		k_dispatch_runs<true><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(k, m, B.d_bases, B.d_read_off, B.d_read_end, B.d_kmer_off, n_reads,
-			total_bases, strip_lo, strip_hi, al, B.d_packed, rpb, B.guess_p0, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err);
+			total_bases, strip_lo, strip_hi, al, B.d_packed, rpb, B.guess_p0, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err, tk);
 	} else {
 		static const int nb = per_sm(k_dispatch_runs<false>);
 		const uint64_t cap = (uint64_t)sm_count_() * limit_per_sm(nb);
 		k_dispatch_runs<false><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(k, m, B.d_bases, B.d_read_off, B.d_read_end, nullptr, n_reads,
-			total_bases, strip_lo, strip_hi, al, B.d_packed, rpb, B.guess_p0, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err);
+			total_bases, strip_lo, strip_hi, al, B.d_packed, rpb, B.guess_p0, R, reinterpret_cast<unsigned long long*>(d_counts), d_ctr, d_err, tk);
 	}
 	g_launches++;
 	return finish("k_dispatch_runs");
@@ -720,7 +721,8 @@ int blight_part_lookup_direct(const blight_index* idx, uint32_t world, const voi
 
 int blight::part_lookup_from(const blight_index* idx, uint32_t world, uint32_t rank, const void* const* regions, const uint64_t* d_counts,
                              void* const* ret, void* const* out_ids, const uint64_t* out_caps, uint64_t cap, uint64_t kcap, uint64_t* d_ctr,
-                             void* stream) {
+                             void* stream, uint64_t* d_ticket) {
+	unsigned long long* tk = reinterpret_cast<unsigned long long*>(d_ticket);
 	if (out_ids && (ret || !out_caps)) return fail(BL_ERR_INVALID_ARG, "direct return: pass out_ids + out_caps and no return regions");
 	const uint64_t max_records = (uint64_t)world * cap;
 	if (!idx || !regions || !d_counts || !d_ctr) return fail(BL_ERR_INVALID_ARG, "null argument");
@@ -748,7 +750,7 @@ int blight::part_lookup_from(const blight_index* idx, uint32_t world, uint32_t r
 	do {                                                                                                 \
 		static const int nb = per_sm(k_runs_lookup<IDS, SM>);                                            \
 		const uint64_t cap = (uint64_t)sm_count_() * limit_per_sm(nb);                                   \
-		k_runs_lookup<IDS, SM><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(idx->v, A, cnt, d_ctr); \
+		k_runs_lookup<IDS, SM><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(idx->v, A, cnt, d_ctr, tk); \
 	} while (0)
 	if (ret || out_ids) { if (idx->v.small) BL_LAUNCH(true, true); else BL_LAUNCH(true, false); }
 	else { if (idx->v.small) BL_LAUNCH(false, true); else BL_LAUNCH(false, false); }

@@ -20,7 +20,7 @@
 // issued after its L(i): nobody is still reading the half. No deadlock: every wait depends only on kernels that precede
 // the matching publish in the publisher's own streams.
 // Identifiers return one of two ways (blight_part_config.return_path):
-//   stream    (default) an owner's warp stores its answers as ONE contiguous run of 32-bit slice-local ids into its return
+//   stream    an owner's warp stores its answers as ONE contiguous run of 32-bit slice-local ids into its return
 //             region at the source; the source widens them into its int64 id array in read order through a local side table
 //             (k_scatter_runs), one sub-batch behind, on its own stream. S(i) may start once W(i+1) has passed: every owner
 //             published P(i+1) after its L(i).
@@ -29,9 +29,11 @@
 //             The lookup kernel then issues no remote store at all: on 8 B200s the pushed streams cost the lookups ~5 ms per
 //             480 M k-mers (remote stores hold the issuing warps' memory pipeline; the loads of the scatter pass stall
 //             nobody but the scatter pass, which runs beside the next sub-batch's lookups).
-//   direct    the owner stores int64 ids straight into the source's id array, run by run. No second pass, but the stores are
-//             ~100-byte segments scattered over a multi-GB array: measured on 8 B200s 160 GB/s per GPU (38.8 ms per batch
-//             of 480 M k-mers) against 17.4 ms for counting — kept for two-GPU boxes, where it is free.
+//   direct    (default) the owner stores int64 ids straight into the source's id array, run by run: no second pass, no side
+//             table, no return regions. The stores are ~100-byte segments scattered over a multi-GB array; what made them
+//             slow in the first measurements (38.8 ms per batch of 480 M k-mers on 8 B200s) was not their size but that all
+//             owners, running in step, stored to the SAME source at any moment. With the round-robin chunk order of
+//             k_runs_lookup: 18.0 ms (stream 18.9, pull 22.3 before the on-demand work distribution), counting 14.3.
 // The ranks are processes (torchrun: buffers exchanged as CUDA IPC handles) or devices of one process
 // (blight_comm, comm.cu: peer access).
 #include <cuda_runtime.h>
@@ -85,6 +87,7 @@ __global__ void k_wait_counts(const Mailbox* mb, uint32_t world, uint32_t slot, 
 		__nanosleep(200);
 	}
 	if (rcv) rcv[s] = mb->count[slot][s];
+	if (rcv && s == 0) rcv[kMaxRanks] = 0;  // the lookup kernel's ticket counter
 }
 
 // Where a batch of `total` base positions is cut into sub-batches: pieces of `full`. (Measured and rejected: pieces that shrink
@@ -139,6 +142,7 @@ struct blight_part_session {
 	uint32_t order = BLIGHT_PART_ORDER_SERIAL;
 	bool stream_ret = true;  // 32-bit id streams + scatter pass (stream and pull)
 	bool pull = false;       // ... fetched by the source from the owner's memory instead of pushed by the owner
+	bool tickets = true;     // dispatch / lookup kernels hand their work items out on demand (BLIGHT_PART_TICKETS=0: fixed stride)
 	int split_lookup = 2, split_dispatch = 2;  // overlap order: resident CTAs per SM of either kernel while both run
 	cudaStream_t side_st = nullptr;  // overlap order: the lookups' stream
 	cudaStream_t scat_st = nullptr;  // stream return: the scatter pass
@@ -181,11 +185,12 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 	}
 	uint32_t rp = cfg->return_path;
 	if (rp == BLIGHT_PART_RETURN_DEFAULT) {
-		rp = BLIGHT_PART_RETURN_STREAM;
+		rp = BLIGHT_PART_RETURN_DIRECT;
 		if (const char* e = getenv("BLIGHT_PART_RETURN"))
 			rp = e[0] == 'd' ? BLIGHT_PART_RETURN_DIRECT : (e[0] == 'p' ? BLIGHT_PART_RETURN_PULL : BLIGHT_PART_RETURN_STREAM);
 	}
 	if (rp != BLIGHT_PART_RETURN_STREAM && rp != BLIGHT_PART_RETURN_DIRECT && rp != BLIGHT_PART_RETURN_PULL) { delete s; return fail(BL_ERR_INVALID_ARG, "unknown return path"); }
+	if (const char* e = getenv("BLIGHT_PART_TICKETS")) s->tickets = e[0] != '0';
 	s->stream_ret = rp != BLIGHT_PART_RETURN_DIRECT;
 	s->pull = rp == BLIGHT_PART_RETURN_PULL;
 	const size_t inbox_bytes = (size_t)2 * cfg->world * s->region_bytes;
@@ -199,9 +204,10 @@ int blight_part_session_create(const blight_index* idx, const blight_part_config
 		if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->side), (size_t)2 * cfg->world * cfg->cap * sizeof(uint4));
 	}
 	for (int b = 0; b < 2 && e == cudaSuccess; b++) {
-		e = cudaMalloc(reinterpret_cast<void**>(&s->counts[b]), kMaxRanks * 8);
-		if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->rcv[b]), kMaxRanks * 8);
-		if (e == cudaSuccess) e = cudaMemset(s->rcv[b], 0, kMaxRanks * 8);
+		// one slot more than ranks: the ticket counter of the dispatch (counts) and of the lookup kernel (rcv) of this half
+		e = cudaMalloc(reinterpret_cast<void**>(&s->counts[b]), (kMaxRanks + 1) * 8);
+		if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->rcv[b]), (kMaxRanks + 1) * 8);
+		if (e == cudaSuccess) e = cudaMemset(s->rcv[b], 0, (kMaxRanks + 1) * 8);
 	}
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->err), 4);
 	if (e == cudaSuccess) e = cudaMemset(s->err, 0, 4);
@@ -396,10 +402,11 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 			CU(cudaStreamWaitEvent(st, s->ev_scat[b], 0));
 			scat_pending[b] = false;
 		}
-		CU(cudaMemsetAsync(s->counts[b], 0, kMaxRanks * 8, st));
+		CU(cudaMemsetAsync(s->counts[b], 0, (kMaxRanks + 1) * 8, st));
 		if (i + 1 < sub_cut.size() && n_reads) {
 			int rc = part_dispatch_batch(s->idx->v.k, s->idx->v.m, RB, sub_cut[i], sub_cut[i + 1], &routes[b],
-			                             reinterpret_cast<uint64_t*>(s->counts[b]), d_ctr, s->err, st);
+			                             reinterpret_cast<uint64_t*>(s->counts[b]), d_ctr, s->err, st,
+			                             s->tickets ? reinterpret_cast<uint64_t*>(s->counts[b] + kMaxRanks) : nullptr);
 			if (rc != BL_OK) return rc;
 		}
 		mark('D', i, st);
@@ -422,7 +429,7 @@ int blight::part_session_query_batch(blight_part_session* s, const ReadBatch& RB
 		const int b = (int)(i & 1);
 		const int rc = part_lookup_from(s->idx, world, c.rank, regions[b], reinterpret_cast<const uint64_t*>(s->rcv[b]), stream_ret ? ret_at[b] : nullptr,
 		                                         want_ids && !stream_ret ? out_ids : nullptr, want_ids && !stream_ret ? s->p_ids_cap : nullptr, c.cap,
-		                                         s->kcap, d_ctr, on);
+		                                         s->kcap, d_ctr, on, s->tickets ? reinterpret_cast<uint64_t*>(s->rcv[b] + kMaxRanks) : nullptr);
 		mark('L', i, on);
 		return rc;
 	};

@@ -35,11 +35,11 @@ import torch.distributed as dist
 from . import api
 
 
-# base positions per sub-batch of the fused path when the caller does not say: counting wants few, large sub-batches (fewer
-# persistent-kernel tails and flag rounds: 7.0x one GPU at 256 M on 8 B200s against 6.5x at 32 M); with ids the scatter of a
-# sub-batch runs one sub-batch behind, so the last one is exposed and smaller is better (5.3x at 32 M, 5.0x at 256 M)
+# base positions per sub-batch of the fused path when the caller does not say: few, large sub-batches (fewer kernel ends and
+# flag rounds). On 8 B200s, 480 M k-mers per GPU: counting 15.2 / 14.6 / 14.3 / 14.2 ms at 32 / 64 / 128 / 256 M; ids on the
+# default direct return path 19.5 / 18.4 / 18.0 ms at 32 / 64 / 128 M (profiles/r02_v18_bench_n8.json)
 DEFAULT_SUB_COUNTING = 256 << 20
-DEFAULT_SUB_IDS = 64 << 20
+DEFAULT_SUB_IDS = 128 << 20
 DEFAULT_ORDER = "serial"  # kernel order of the fused partitioned path when neither the caller nor BLIGHT_PART_ORDER says (part_session.cu)
 
 

@@ -262,7 +262,7 @@ typedef struct blight_part_config {
 	uint64_t ret_kmers;                  /* stream return: ids per (owner, sub-batch) region; 0 = sub_positions (can never overflow);
 	                                        smaller saves memory, a sub-batch sending one owner more raises BLIGHT_PART_OVERFLOW */
 } blight_part_config;
-#define BLIGHT_PART_RETURN_DEFAULT 0u /* what BLIGHT_PART_RETURN says (stream | pull | direct), else the library's choice */
+#define BLIGHT_PART_RETURN_DEFAULT 0u /* what BLIGHT_PART_RETURN says (stream | pull | direct), else direct */
 #define BLIGHT_PART_RETURN_STREAM 1u  /* contiguous 32-bit id streams per owner warp + a scatter pass at the source */
 #define BLIGHT_PART_RETURN_DIRECT 2u  /* int64 ids stored by the owner straight into the source's id array */
 #define BLIGHT_PART_RETURN_PULL 3u    /* as STREAM, but the streams stay in the owner's memory and the source's scatter pass fetches them */
