@@ -50,14 +50,6 @@ int ensure_device(int device) {
 	cudaError_t e = cudaGetDeviceCount(&n);
 	if (e != cudaSuccess || n == 0) return fail(BL_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
 	if (device < 0 || device >= n) return fail(BL_ERR_INVALID_ARG, "device ordinal out of range");
-	// experiment knob: how much the L2 fetches from HBM around a missed 32-byte sector (32 / 64 / 128 bytes; the driver's default is 64)
-	if (const char* g = getenv("BLIGHT_L2_FETCH")) {
-		int prev = -1;
-		cudaGetDevice(&prev);
-		cudaSetDevice(device);
-		if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)) != cudaSuccess) cudaGetLastError();
-		if (prev >= 0 && prev != device) cudaSetDevice(prev);
-	}
 	return BL_OK;
 }
 

@@ -140,7 +140,7 @@ int partition_batch(blight_comm* c, const char* text, const uint64_t* beg, const
 	if (!c->sess[0] || (want_ids && c->ids_cap < max_kmers)) {
 		const double rpp = std::min(0.25, std::max(0.03, 0.5 / W));
 		const uint64_t max_cap = (1ull << 24) - 1;
-		uint64_t sub = std::min<uint64_t>(32ull << 20, uint64_t(max_cap / rpp)) / kReadsStrip * kReadsStrip;
+		uint64_t sub = std::min<uint64_t>(64ull << 20, uint64_t(max_cap / rpp)) / kReadsStrip * kReadsStrip;  // 8 B200s, 480 M k-mers per GPU: ids 19.5 / 18.4 / 18.0 ms at 32 / 64 / 128 M
 		if (c->sub) sub = c->sub;
 		uint64_t cap = c->cap ? c->cap : std::min<uint64_t>(std::max<uint64_t>(1024, uint64_t(sub * rpp)), max_cap);
 		if (const char* e = getenv("BLIGHT_PART_CAP")) { const uint64_t v = strtoull(e, nullptr, 10); if (v && !c->cap) cap = std::min(v, max_cap); }  // test knob
