@@ -268,10 +268,11 @@ def run_reference(args, rank):
     kmers = n_reads * (args.read_len - args.k + 1)
     for _ in range(args.warmup):
         ref.query_reads(rb[: ro[2000]], ro[:2001], threads=threads, want_ids=False)
-    t = 0.0
+    t, step_s = 0.0, []
     for _ in range(args.steps):
         _, f, nf, sec = ref.query_reads(rb, ro, threads=threads, want_ids=False)
         t += sec
+        step_s.append(round(sec, 4))
     val = kmers * args.steps / t
     _, fq = reference_measure(blob, args.k, args.m, rb, n_reads, args.read_len, warm=False)
     os.remove(blob)
@@ -287,6 +288,7 @@ def run_reference(args, rank):
                          "file_query": fq},
         "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "found": f, "not_found": nf, "product_library_mapped": bool(mapped),
+        "step_seconds": step_s, "host": {"cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0)), "loadavg": os.getloadavg()},
     }
     emit(line)
 

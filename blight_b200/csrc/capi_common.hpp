@@ -1,5 +1,6 @@
 // capi_common.hpp — definitions shared by the two halves of the C ABI (capi_host.cpp, capi_device.cu).
 #pragma once
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -21,6 +22,11 @@ int build_flat_index_gpu(const char* text, uint64_t text_len, const std::vector<
 // stream_query.cu: file_query(path) chunk by chunk (reader thread -> parallel record cut -> H2D / kernel overlap)
 int stream_file_query(const struct ::blight_index* idx, const char* path, uint64_t* ctr);
 void stream_ctx_free(void* ctx);
+// the same reader and record cut for a consumer that is done with a batch when it returns (comm.cu: several GPUs). *host holds
+// the pinned buffers, created on first use and kept by the caller until stream_host_free
+int stream_fasta_chunks(const char* path, void** host,
+                        const std::function<int(const char* text, uint64_t len, const uint64_t* beg, const uint64_t* end, uint64_t n_rec)>& on_batch);
+void stream_host_free(void* host);
 // host_query.cu: the contexts of the host-buffer entry points, created on first use and kept with the index
 void host_pool_free(void* pool);
 // a batch of records of a text in host memory ([beg[i], end[i]), beg has n+1 entries; end == null: end[i] = beg[i+1]) through

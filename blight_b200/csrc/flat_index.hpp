@@ -88,7 +88,14 @@ void split_fasta_records(const char* text, uint64_t len, std::vector<SeqView>& s
 // the number of line pairs, an upper bound of the records; fasta_chunk_records fills beg[0..n_rec) / end[0..n_rec) with
 // the sequence lines (offsets into text).
 struct ChunkCut { size_t n_rec, consumed; };
-size_t fasta_chunk_lines(const char* text, size_t len, bool eof, std::vector<uint64_t>& nl);
-ChunkCut fasta_chunk_records(size_t len, bool eof, const std::vector<uint64_t>& nl, uint64_t* beg, uint64_t* end);
+// newline offsets (from `text`) of text[lo, hi) written to out[n...], n advanced; out grows as needed and is never shrunk
+void scan_newlines(const char* text, size_t lo, size_t hi, std::vector<uint64_t>& out, size_t& n);
+// fasta_chunk_lines when the new data (text + head_len .. text + len) was already scanned in n_parts consecutive slices:
+// parts[i][0..counts[i]) = newline offsets from the start of the NEW data; the carried head text[0, head_len) is scanned here
+size_t fasta_chunk_lines_merge(const char* text, size_t head_len, size_t len, bool eof, const std::vector<uint64_t>* parts, const size_t* counts,
+                               int n_parts, std::vector<uint64_t>& nl, int threads = 0);
+// threads: size of the OpenMP team (0: all host threads)
+size_t fasta_chunk_lines(const char* text, size_t len, bool eof, std::vector<uint64_t>& nl, int threads = 0);
+ChunkCut fasta_chunk_records(size_t len, bool eof, const std::vector<uint64_t>& nl, uint64_t* beg, uint64_t* end, int threads = 0);
 
 }  // namespace blight
