@@ -28,7 +28,7 @@ SYMBOLS = [
     "blight_query_sequence_bool_host", "blight_transfer_bytes", "blight_host_pack_stats",
     "blight_query_fasta_host", "blight_query_file_host", "blight_query_sequence_host", "blight_query_reads_host",
     "blight_query_kmers_host", "blight_owner_count", "blight_owner_scatter", "blight_scatter_ids", "blight_launch_count",
-    "blight_consume_reads", "blight_gather_reads", "blight_fasta_cut_stream", "blight_part_dispatch", "blight_part_lookup", "blight_part_lookup_direct", "blight_part_scatter",
+    "blight_consume_reads", "blight_gather_reads", "blight_fasta_cut_stream", "blight_fasta_cut_stream_parts", "blight_part_dispatch", "blight_part_lookup", "blight_part_lookup_direct", "blight_part_scatter",
     "blight_part_session_create", "blight_part_session_free", "blight_part_session_handles", "blight_part_session_connect_ipc",
     "blight_part_session_connect_local", "blight_part_session_ids", "blight_part_session_sub_batches", "blight_part_session_query", "blight_part_session_status",
     "blight_comm_init", "blight_comm_free", "blight_comm_describe", "blight_comm_query_reads_host", "blight_comm_query_fasta_host",
@@ -154,6 +154,7 @@ def lib() -> C.CDLL:
     L.blight_scatter_ids.argtypes = [vp, vp, u64, vp, vp]
     L.blight_launch_count.restype = u64
     L.blight_fasta_cut_stream.argtypes = [vp, u64, u64, vp, vp, u64, C.POINTER(u64)]
+    L.blight_fasta_cut_stream_parts.argtypes = [vp, u64, u64, u32, vp, vp, u64, C.POINTER(u64)]
     L.blight_consume_reads.argtypes = [vp, vp, vp, u64, u64, C.c_int, vp, u32, u32, vp, vp]
     L.blight_gather_reads.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp]
     L.blight_part_dispatch.argtypes = [u32, u32, vp, vp, vp, u64, u64, u64, u64, C.POINTER(PartRoute), vp, vp, vp, vp]

@@ -132,17 +132,37 @@ int blight_flat_slice(const blight_flat* f, uint64_t g_begin, uint64_t g_end, bl
 
 int blight_fasta_cut_stream(const char* text, uint64_t len, uint64_t chunk_bytes, uint64_t* beg_out, uint64_t* end_out, uint64_t cap,
                             uint64_t* n_out) {
-	if (!n_out || (len && !text) || chunk_bytes == 0) return fail(BL_ERR_INVALID_ARG, "bad argument");
-	// the loop of stream_file_query (stream_query.cu) on a text in memory: chunks of chunk_bytes, unfinished tail carried
+	return blight_fasta_cut_stream_parts(text, len, chunk_bytes, 0, beg_out, end_out, cap, n_out);
+}
+
+int blight_fasta_cut_stream_parts(const char* text, uint64_t len, uint64_t chunk_bytes, uint32_t reader_slices, uint64_t* beg_out,
+                                  uint64_t* end_out, uint64_t cap, uint64_t* n_out) {
+	if (!n_out || (len && !text) || chunk_bytes == 0 || reader_slices > 4096) return fail(BL_ERR_INVALID_ARG, "bad argument");
+	// the loop of stream_file_query (stream_query.cu) on a text in memory: chunks of chunk_bytes, unfinished tail carried.
+	// reader_slices > 0: as the streaming reader does it — the NEW bytes of every chunk are scanned for newlines in that many
+	// consecutive slices (offsets from the start of the new data), the carried head is scanned at the merge.
 	std::vector<char> buf;
 	std::vector<uint64_t> nl, beg, end;
+	std::vector<std::vector<uint64_t>> parts(reader_slices);
+	std::vector<size_t> part_n(reader_slices);
 	uint64_t n = 0, file_off = 0, buf_file_off = 0;
 	for (;;) {
 		const uint64_t got = std::min<uint64_t>(chunk_bytes, len - file_off);
+		const size_t head = buf.size();
 		buf.insert(buf.end(), text + file_off, text + file_off + got);
 		file_off += got;
 		const bool eof = file_off >= len;
-		const size_t n_pairs = fasta_chunk_lines(buf.data(), buf.size(), eof, nl);
+		size_t n_pairs;
+		if (reader_slices) {
+			for (uint32_t t = 0; t < reader_slices; t++) {
+				size_t cnt = 0;
+				scan_newlines(buf.data() + head, got * t / reader_slices, got * (t + 1) / reader_slices, parts[t], cnt);
+				part_n[t] = cnt;
+			}
+			n_pairs = fasta_chunk_lines_merge(buf.data(), head, buf.size(), eof, parts.data(), part_n.data(), (int)reader_slices, nl);
+		} else {
+			n_pairs = fasta_chunk_lines(buf.data(), buf.size(), eof, nl);
+		}
 		beg.resize(n_pairs + 1); end.resize(n_pairs + 1);
 		const ChunkCut cut = fasta_chunk_records(buf.size(), eof, nl, beg.data(), end.data());
 		for (size_t i = 0; i < cut.n_rec; i++, n++)

@@ -334,6 +334,10 @@ int blight_comm_query_sequence_host(blight_comm* c, const char* seq, uint64_t le
  * (blight.cpp:760-772). *n_out = records found (may exceed cap; only the first cap are stored). */
 int blight_fasta_cut_stream(const char* text, uint64_t len, uint64_t chunk_bytes, uint64_t* beg_out, uint64_t* end_out,
                             uint64_t cap, uint64_t* n_out);
+/* The same with the newline search done the way the streaming reader does it: the new bytes of every chunk scanned in
+ * reader_slices consecutive slices (one per reader thread), the lists merged behind the carried tail (0: one scan per chunk). */
+int blight_fasta_cut_stream_parts(const char* text, uint64_t len, uint64_t chunk_bytes, uint32_t reader_slices, uint64_t* beg_out,
+                                  uint64_t* end_out, uint64_t cap, uint64_t* n_out);
 
 /* Bytes the host-buffer entry points copied host->device and device->host in the calling process since load. */
 void blight_transfer_bytes(uint64_t* h2d, uint64_t* d2h);

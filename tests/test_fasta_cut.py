@@ -34,14 +34,16 @@ def reference_records(text: bytes):
     return out
 
 
-def cut(text: bytes, chunk: int):
+def cut(text: bytes, chunk: int, slices: int = 0):
+    """slices > 0: the newline search as the streaming reader does it (every chunk's new bytes scanned in that many slices,
+    lists merged behind the carried tail: flat_index.cpp fasta_chunk_lines_merge)."""
     L = api.lib()
     buf = np.frombuffer(text, dtype=np.uint8) if text else np.zeros(0, dtype=np.uint8)
     cap = len(text) // 2 + 2
     beg = np.zeros(cap, dtype=np.uint64)
     end = np.zeros(cap, dtype=np.uint64)
     n = C.c_uint64()
-    rc = L.blight_fasta_cut_stream(buf.ctypes.data if len(buf) else None, len(buf), chunk, beg.ctypes.data, end.ctypes.data, cap, C.byref(n))
+    rc = L.blight_fasta_cut_stream_parts(buf.ctypes.data if len(buf) else None, len(buf), chunk, slices, beg.ctypes.data, end.ctypes.data, cap, C.byref(n))
     assert rc == 0, L.blight_last_error()
     return [(int(beg[i]), int(end[i])) for i in range(n.value)]
 
@@ -53,6 +55,8 @@ def test_known_cases():
         want = reference_records(t)
         for chunk in (1, 2, 3, 5, 7, 64, 1 << 20):
             assert cut(t, chunk) == want, (t[:40], chunk)
+            for slices in (1, 3, 12):
+                assert cut(t, chunk, slices) == want, (t[:40], chunk, slices)
 
 
 @settings(max_examples=300, deadline=None)
@@ -60,6 +64,27 @@ def test_known_cases():
 def test_any_text_any_chunk(lines, trailing_newline, chunk):
     text = b"\n".join(lines) + (b"\n" if trailing_newline and lines else b"")
     assert cut(text, chunk) == reference_records(text)
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.sampled_from([b"", b">r", b"ACGT", b"A", b"GGGTTTAAACCC" * 9, b">", b"x"]), max_size=40), st.booleans(), st.integers(1, 400),
+       st.integers(1, 16))
+def test_any_text_any_chunk_reader_slices(lines, trailing_newline, chunk, slices):
+    text = b"\n".join(lines) + (b"\n" if trailing_newline and lines else b"")
+    assert cut(text, chunk, slices) == reference_records(text)
+
+
+def test_large_text_parallel_cut():
+    """Sizes at which the cut runs its multi-threaded paths (4096 pairs and up), with and without reader slices."""
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(20000):
+        recs.append(b">r%d" % i if rng.random() > 0.01 else b"")
+        recs.append(b"ACGT" * int(rng.integers(0, 40)))
+    text = b"\n".join(recs) + b"\n"
+    want = reference_records(text)
+    for chunk, slices in ((1 << 30, 0), (1 << 30, 12), (200_000, 0), (200_000, 5), (65_537, 16)):
+        assert cut(text, chunk, slices) == want, (chunk, slices)
 
 
 def test_cut_plus_oracle_equals_the_reference_file_query(tmp_path):
