@@ -13,15 +13,20 @@
 //   k_runs_lookup     (on the owner)  per warp 32 consecutive records of one source: the first k-mer of every run
 //                     through the whole lookup (lookup.cuh), every other k-mer of the run against the ONE window next
 //                     to where the first one matched (answer = pos_id / valid of that window, device_index.hpp), the
-//                     rest through the negative filter and the whole lookup. The warp's ids (32-bit) are collected in
-//                     shared memory and STORED DIRECTLY into the source GPU's return region as one contiguous,
-//                     sector-aligned stream (first version: 8-byte stores scattered into the source's id buffer reached
-//                     only 73 GB/s of NVLink). In counting mode nothing travels back but two counters.
-//   k_scatter_runs    (back on the source)  return streams -> int64 ids in read order, through the side table.
+//                     rest through the negative filter and the whole lookup. The warp's ids are collected in shared memory
+//                     and return one of three ways (part_session.cu): int64 ids STORED DIRECTLY into the source GPU's id
+//                     array, run by run (default); or as one contiguous, sector-aligned stream of 32-bit ids into the
+//                     source's return region (or the owner's own memory: pull), widened into read order by
+//                     k_scatter_runs. In counting mode nothing travels back but two counters.
+//                     Owners take their sources ROUND-ROBIN, starting at their right-hand neighbour: taking them one after
+//                     the other made all owners (they run in step) return ids to the SAME GPU at any moment.
+//   k_scatter_runs    (back on the source, stream / pull return)  return streams -> int64 ids in read order, through the
+//                     side table.
 //
-// Ordering between GPUs is the caller's (blight_b200/dist.py): one tiny NCCL all-to-all of the per-pair counters
-// between dispatch and lookup (it is also the barrier that publishes the records; the one of the NEXT sub-batch
-// publishes the returned ids), one all-reduce of the counters at the end of a batch.
+// Both persistent kernels hand their work items out on demand (front.cuh: next_item) when the caller passes a zeroed ticket
+// counter. Ordering between GPUs is the session's (part_session.cu): device-side flags in peer memory, no collective call on
+// the data path; the round-1 Python pipeline (blight_b200/dist.py, BLIGHT_PART_PIPELINE=legacy: one tiny NCCL all-to-all of
+// the per-pair counters per sub-batch) still drives the same kernels through the C ABI entry points below.
 #include <cuda_runtime.h>
 
 #include <cstring>
